@@ -1,0 +1,519 @@
+// abi.cu - the extern "C" boundary of libacro_b200.so (include/acro_b200.h):
+// handle management, argument validation, error reporting, the host-buffer
+// pipeline and the FMA-peak micro-benchmark.  No kernels of the hot path live
+// here; see fk.cu, fk_cc.cu, jac_ik.cu, path.cu.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "acro_launch.h"
+
+using namespace acro;
+
+struct AcroRobot {
+  AcroRobotDesc desc;
+  RobotDev<double> d64;
+  RobotDev<float> d32;
+};
+
+struct AcroScene {
+  int32_t n;
+  int device;
+  double* dev64;
+  float* dev32;
+};
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+
+bool is_identity_rot(const double* m) {
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (m[4 * r + c] != I[3 * r + c]) return false;
+  return true;
+}
+
+bool is_identity_tf(const double* m) {
+  return is_identity_rot(m) && m[3] == 0.0 && m[7] == 0.0 && m[11] == 0.0;
+}
+
+template <typename real>
+int build_dev(const AcroRobotDesc& d, RobotDev<real>& o) {
+  std::memset(&o, 0, sizeof(o));
+  const int n = d.ndof;
+  o.ndof = n;
+  o.has_tool_tip = d.has_tool_tip;
+  o.check_self = d.check_self;
+  o.n_boxes = d.n_boxes;
+  o.base_identity = is_identity_tf(d.tf_base);
+  for (int i = 0; i < n; ++i) {
+    if (d.joint_type[i]) o.prismatic_mask |= 1 << i;
+    o.a[i] = (real)d.a[i];
+    o.d[i] = (real)d.d[i];
+    o.theta[i] = (real)d.theta[i];
+    o.ca[i] = (real)d.cos_alpha[i];
+    o.sa[i] = (real)d.sin_alpha[i];
+  }
+  for (int k = 0; k < 12; ++k) {
+    o.base[k] = (real)d.tf_base[k];
+    o.tip[k] = (real)d.tf_tool_tip[k];
+  }
+  // processing order: base boxes, link 0..n-1 boxes, tool boxes
+  auto slot_of = [&](int carrier) {
+    if (carrier == ACRO_CARRIER_BASE) return 0;
+    if (carrier == ACRO_CARRIER_TOOL) return n + 1;
+    return carrier + 1;
+  };
+  std::vector<int> order;
+  for (int s = 0; s <= n + 1; ++s) {
+    o.slot_begin[s] = (int)order.size();
+    for (int b = 0; b < d.n_boxes; ++b)
+      if (slot_of(d.boxes[b].carrier) == s) order.push_back(b);
+  }
+  o.slot_begin[n + 2] = (int)order.size();
+  std::vector<int> new_index(d.n_boxes, -1);
+  for (int k = 0; k < (int)order.size(); ++k) new_index[order[k]] = k;
+  for (int k = 0; k < (int)order.size(); ++k) {
+    const AcroRobotBox& src = d.boxes[order[k]];
+    BoxDev<real>& bx = o.boxes[k];
+    double r2 = 0;
+    for (int e = 0; e < 3; ++e) {
+      bx.half[e] = (real)src.half[e];
+      r2 += src.half[e] * src.half[e];
+    }
+    // round the bounding radius up so that the sphere really contains the box
+    bx.radius = (real)(std::sqrt(r2) * (1.0 + 1e-6));
+    for (int e = 0; e < 12; ++e) bx.off[e] = (real)src.tf[e];
+    bx.rot_identity = is_identity_rot(src.tf);
+    bx.save_slot = -1;
+  }
+  // self pairs grouped by their later box (in processing order)
+  std::vector<std::vector<int>> partners(d.n_boxes);
+  int n_saved = 0;
+  for (int p = 0; p < d.n_self_pairs; ++p) {
+    const int b1 = new_index[d.self_pairs[p][0]], b2 = new_index[d.self_pairs[p][1]];
+    const int lo = b1 < b2 ? b1 : b2, hi = b1 < b2 ? b2 : b1;
+    partners[hi].push_back(lo);
+    if (o.boxes[lo].save_slot < 0) {
+      if (n_saved >= kMaxSaved) return -1;
+      o.boxes[lo].save_slot = n_saved++;
+    }
+  }
+  int cursor = 0;
+  for (int b = 0; b < d.n_boxes; ++b) {
+    o.pair_begin[b] = (uint8_t)cursor;
+    for (int lo : partners[b]) o.partner[cursor++] = (uint8_t)lo;
+  }
+  for (int b = d.n_boxes; b <= kMaxBoxes; ++b) o.pair_begin[b] = (uint8_t)cursor;
+  return 0;
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename real>
+SceneView<real> view_of(const AcroScene* sc);
+template <>
+SceneView<double> view_of<double>(const AcroScene* sc) {
+  return sc ? SceneView<double>{sc->dev64, sc->n} : SceneView<double>{nullptr, 0};
+}
+template <>
+SceneView<float> view_of<float>(const AcroScene* sc) {
+  return sc ? SceneView<float>{sc->dev32, sc->n} : SceneView<float>{nullptr, 0};
+}
+
+int check_batch(const void* robot, const void* in, const void* out, int64_t n) {
+  if (!robot) return fail(ACRO_E_INVALID, "robot handle is NULL");
+  if (n < 0) return fail(ACRO_E_INVALID, "negative batch size");
+  if (n > 0 && (!in || !out)) return fail(ACRO_E_INVALID, "NULL buffer for a non-empty batch");
+  return 0;
+}
+
+int finish(cudaError_t e, const char* where) { return e == cudaSuccess ? 0 : cuda_fail(e, where); }
+
+}  // namespace
+
+namespace acro {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace acro
+
+extern "C" {
+
+int acro_abi_version(void) { return ACRO_ABI_VERSION; }
+
+const char* acro_last_error(void) { return g_err.c_str(); }
+
+int64_t acro_launch_count(void) { return g_launches.load(); }
+
+int acro_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  return n;
+}
+
+int acro_robot_create(const AcroRobotDesc* desc, AcroRobot** out) {
+  if (!desc || !out) return fail(ACRO_E_INVALID, "NULL argument");
+  *out = nullptr;
+  if (desc->ndof < 1 || desc->ndof > ACRO_MAX_DOF)
+    return fail(ACRO_E_UNSUPPORTED, "ndof outside 1..ACRO_MAX_DOF");
+  if (desc->n_boxes < 0 || desc->n_boxes > ACRO_MAX_ROBOT_BOXES)
+    return fail(ACRO_E_UNSUPPORTED, "too many robot boxes");
+  if (desc->n_self_pairs < 0 || desc->n_self_pairs > ACRO_MAX_SELF_PAIRS)
+    return fail(ACRO_E_UNSUPPORTED, "too many self-collision pairs");
+  for (int i = 0; i < desc->ndof; ++i)
+    if (desc->joint_type[i] != 0 && desc->joint_type[i] != 1)
+      return fail(ACRO_E_INVALID, "unknown joint type");  // link.py:26-29 ValueError
+  for (int b = 0; b < desc->n_boxes; ++b) {
+    const int c = desc->boxes[b].carrier;
+    if (!(c == ACRO_CARRIER_BASE || c == ACRO_CARRIER_TOOL || (c >= 0 && c < desc->ndof)))
+      return fail(ACRO_E_INVALID, "box carrier out of range");
+  }
+  for (int p = 0; p < desc->n_self_pairs; ++p) {
+    const int b1 = desc->self_pairs[p][0], b2 = desc->self_pairs[p][1];
+    if (b1 < 0 || b2 < 0 || b1 >= desc->n_boxes || b2 >= desc->n_boxes || b1 == b2)
+      return fail(ACRO_E_INVALID, "self pair index out of range");
+  }
+  AcroRobot* r = new AcroRobot;
+  r->desc = *desc;
+  if (build_dev<double>(*desc, r->d64) || build_dev<float>(*desc, r->d32)) {
+    delete r;
+    return fail(ACRO_E_UNSUPPORTED, "too many boxes take part in self-collision pairs");
+  }
+  *out = r;
+  return 0;
+}
+
+void acro_robot_destroy(AcroRobot* robot) { delete robot; }
+
+int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
+  if (!out || n < 0 || (n > 0 && !boxes)) return fail(ACRO_E_INVALID, "bad scene arguments");
+  *out = nullptr;
+  if (n > ACRO_MAX_SCENE_BOXES) return fail(ACRO_E_UNSUPPORTED, "too many scene boxes");
+  std::vector<double> p64((size_t)(n > 0 ? n : 1) * kSceneStride, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double* o = &p64[(size_t)j * kSceneStride];
+    double r2 = 0, hmax = 0;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) o[3 * r + c] = boxes[j].tf[4 * r + c];
+      o[9 + r] = boxes[j].tf[4 * r + 3];
+      o[12 + r] = boxes[j].half[r];
+      r2 += boxes[j].half[r] * boxes[j].half[r];
+      hmax = boxes[j].half[r] > hmax ? boxes[j].half[r] : hmax;
+    }
+    o[15] = std::sqrt(r2) * (1.0 + 1e-6);
+    o[16] = hmax;
+  }
+  std::vector<float> p32(p64.size());
+  for (size_t k = 0; k < p64.size(); ++k) p32[k] = (float)p64[k];
+  AcroScene* s = new AcroScene{n, 0, nullptr, nullptr};
+  cudaError_t e = cudaGetDevice(&s->device);
+  if (e == cudaSuccess) e = cudaMalloc(&s->dev64, p64.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->dev32, p32.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(s->dev64, p64.data(), p64.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(s->dev32, p32.data(), p32.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(s->dev64);
+    cudaFree(s->dev32);
+    delete s;
+    cudaGetLastError();
+    return cuda_fail(e, "acro_scene_create");
+  }
+  *out = s;
+  return 0;
+}
+
+void acro_scene_destroy(AcroScene* scene) {
+  if (!scene) return;
+  cudaFree(scene->dev64);
+  cudaFree(scene->dev32);
+  delete scene;
+}
+
+int acro_collide_boxes_f64(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,
+                           void* stream) {
+  if (n < 0 || (n > 0 && (!a || !b || !mask))) return fail(ACRO_E_INVALID, "bad arguments");
+  return finish(launch_collide_boxes(a, b, n, mask, as_stream(stream)),
+                "acro_collide_boxes_f64");
+}
+
+int acro_fk_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                double* T_out, int32_t all_links, void* stream) {
+  if (int rc = check_batch(robot, q, T_out, n)) return rc;
+  return finish(launch_fk<double>(robot->d64, q, n, q_layout, T_out, all_links != 0,
+                                  as_stream(stream)),
+                "acro_fk_f64");
+}
+
+int acro_fk_f32(const AcroRobot* robot, const float* q, int64_t n, int32_t q_layout, float* T_out,
+                int32_t all_links, void* stream) {
+  if (int rc = check_batch(robot, q, T_out, n)) return rc;
+  return finish(
+      launch_fk<float>(robot->d32, q, n, q_layout, T_out, all_links != 0, as_stream(stream)),
+      "acro_fk_f32");
+}
+
+int acro_fk_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                    double* out, void* stream) {
+  if (int rc = check_batch(robot, q, out, n)) return rc;
+  return finish(launch_fk_rpy(robot->d64, q, n, q_layout, out, as_stream(stream)),
+                "acro_fk_rpy_f64");
+}
+
+int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
+                   int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
+                   void* stream) {
+  if (int rc = check_batch(robot, q, mask, n)) return rc;
+  if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
+  return finish(launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, q_layout, mask,
+                                     near_mask, margin, as_stream(stream)),
+                "acro_fk_cc_f64");
+}
+
+int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
+                   int32_t q_layout, uint32_t* mask, void* stream) {
+  if (int rc = check_batch(robot, q, mask, n)) return rc;
+  return finish(launch_fk_cc<float>(robot->d32, view_of<float>(scene), q, n, q_layout, mask,
+                                    nullptr, 0.f, as_stream(stream)),
+                "acro_fk_cc_f32");
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer pipeline: chunked H2D -> K2 -> D2H over kSlots rotating slots
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kSlots = 3;
+struct HostPipe {
+  std::mutex mu;
+  int device = -1;
+  int64_t chunk = 0;
+  int ndof = 0;
+  double* d_q[kSlots] = {};
+  uint32_t* d_mask[kSlots] = {};
+  cudaStream_t st[kSlots] = {};
+  void release() {
+    for (int s = 0; s < kSlots; ++s) {
+      if (d_q[s]) cudaFree(d_q[s]);
+      if (d_mask[s]) cudaFree(d_mask[s]);
+      if (st[s]) cudaStreamDestroy(st[s]);
+      d_q[s] = nullptr;
+      d_mask[s] = nullptr;
+      st[s] = nullptr;
+    }
+    chunk = 0;
+  }
+};
+HostPipe g_pipe;
+}  // namespace
+
+int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
+                        int64_t n, uint32_t* mask_host, int64_t chunk) {
+  if (int rc = check_batch(robot, q_host, mask_host, n)) return rc;
+  if (n == 0) return 0;
+  if (chunk <= 0) chunk = 1 << 22;
+  chunk = (chunk + 31) / 32 * 32;  // chunk boundaries fall on mask words
+  if (chunk > n) chunk = (n + 31) / 32 * 32;
+  const int ndof = robot->d64.ndof;
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (g_pipe.device != dev || g_pipe.chunk < chunk || g_pipe.ndof < ndof) {
+    g_pipe.release();
+    for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
+      e = cudaMalloc(&g_pipe.d_q[s], sizeof(double) * chunk * ndof);
+      if (e == cudaSuccess) e = cudaMalloc(&g_pipe.d_mask[s], sizeof(uint32_t) * (chunk / 32));
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_pipe.st[s], cudaStreamNonBlocking);
+    }
+    if (e != cudaSuccess) {
+      g_pipe.release();
+      cudaGetLastError();
+      return cuda_fail(e, "acro_fk_cc_f64_host workspace");
+    }
+    g_pipe.device = dev;
+    g_pipe.chunk = chunk;
+    g_pipe.ndof = ndof;
+  }
+  int64_t done = 0;
+  int slot = 0;
+  while (done < n && e == cudaSuccess) {
+    const int64_t m = (n - done) < chunk ? (n - done) : chunk;
+    cudaStream_t st = g_pipe.st[slot];
+    // work queued on a stream is ordered, so reusing the slot's buffers is safe
+    e = cudaMemcpyAsync(g_pipe.d_q[slot], q_host + done * ndof, sizeof(double) * m * ndof,
+                        cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+      e = launch_fk_cc<double>(robot->d64, view_of<double>(scene), g_pipe.d_q[slot], m,
+                               ACRO_Q_AOS, g_pipe.d_mask[slot], nullptr, 0.0, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(mask_host + done / 32, g_pipe.d_mask[slot],
+                          sizeof(uint32_t) * ((m + 31) / 32), cudaMemcpyDeviceToHost, st);
+    done += m;
+    slot = (slot + 1) % kSlots;
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    cudaError_t e2 = cudaStreamSynchronize(g_pipe.st[s]);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_fk_cc_f64_host");
+}
+
+int acro_jac_pos_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                     double* J_out, void* stream) {
+  if (int rc = check_batch(robot, q, J_out, n)) return rc;
+  return finish(launch_jac(robot->d64, q, n, q_layout, J_out, false, as_stream(stream)),
+                "acro_jac_pos_f64");
+}
+
+int acro_jac_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                     double* J_out, void* stream) {
+  if (int rc = check_batch(robot, q, J_out, n)) return rc;
+  return finish(launch_jac(robot->d64, q, n, q_layout, J_out, true, as_stream(stream)),
+                "acro_jac_rpy_f64");
+}
+
+static int check_kuka(const AcroRobot* robot) {
+  if (!robot) return fail(ACRO_E_INVALID, "robot handle is NULL");
+  if (robot->d64.ndof != 6 || robot->d64.prismatic_mask != 0)
+    return fail(ACRO_E_UNSUPPORTED, "Kuka IK needs a 6-dof all-revolute chain");
+  return 0;
+}
+
+int acro_ik_kuka_f64(const AcroRobot* robot, const double* T, int64_t n, double* q_out,
+                     uint8_t* valid, void* stream) {
+  if (int rc = check_kuka(robot)) return rc;
+  if (int rc = check_batch(robot, T, q_out, n)) return rc;
+  if (n > 0 && !valid) return fail(ACRO_E_INVALID, "valid is NULL");
+  return finish(launch_ik_kuka(robot->d64, T, n, q_out, valid, as_stream(stream)),
+                "acro_ik_kuka_f64");
+}
+
+int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* T, int64_t n,
+                        double* q_out, uint8_t* valid, uint8_t* free_mask, void* stream) {
+  if (int rc = check_kuka(robot)) return rc;
+  if (int rc = check_batch(robot, T, q_out, n)) return rc;
+  if (n > 0 && (!valid || !free_mask)) return fail(ACRO_E_INVALID, "valid/free_mask is NULL");
+  return finish(launch_ik_kuka_cc(robot->d64, view_of<double>(scene), T, n, q_out, valid,
+                                  free_mask, as_stream(stream)),
+                "acro_ik_kuka_cc_f64");
+}
+
+int acro_ik_arm2_f64(double a1, double a2, double a3, const double* p, int64_t n, double* q_out,
+                     uint8_t* valid, void* stream) {
+  if (n < 0 || (n > 0 && (!p || !q_out || !valid))) return fail(ACRO_E_INVALID, "bad arguments");
+  return finish(launch_ik_arm2(a1, a2, a3, p, n, q_out, valid, as_stream(stream)),
+                "acro_ik_arm2_f64");
+}
+
+int acro_ik_anthropomorphic_f64(double l2, double l3, const double* p, int64_t n, double* q_out,
+                                uint8_t* valid, void* stream) {
+  if (n < 0 || (n > 0 && (!p || !q_out || !valid))) return fail(ACRO_E_INVALID, "bad arguments");
+  return finish(launch_ik_anthro(l2, l3, p, n, q_out, valid, as_stream(stream)),
+                "acro_ik_anthropomorphic_f64");
+}
+
+int acro_ik_wrist_f64(const double* R, const double* R_base_host, int64_t n, double* q_out,
+                      void* stream) {
+  if (n < 0 || !R_base_host || (n > 0 && (!R || !q_out)))
+    return fail(ACRO_E_INVALID, "bad arguments");
+  return finish(launch_ik_wrist(R, R_base_host, n, q_out, as_stream(stream)), "acro_ik_wrist_f64");
+}
+
+int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
+                     const double* q_goal, int64_t n_segments, double max_q_step, uint32_t* mask,
+                     void* stream) {
+  if (int rc = check_batch(robot, q_start, mask, n_segments)) return rc;
+  if (n_segments > 0 && !q_goal) return fail(ACRO_E_INVALID, "q_goal is NULL");
+  if (!(max_q_step > 0.0)) return fail(ACRO_E_INVALID, "max_q_step must be > 0");
+  return finish(launch_path_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_segments,
+                               max_q_step, mask, as_stream(stream)),
+                "acro_path_cc_f64");
+}
+
+int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms) {
+  if (!tflops || !ms || iters <= 0) return fail(ACRO_E_INVALID, "bad arguments");
+  return finish(measure_fma_peak(fp64 != 0, iters, tflops, ms), "acro_measure_fma_peak");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// FMA-chain micro-benchmark (compute-roofline denominator)
+// ---------------------------------------------------------------------------
+namespace acro {
+
+template <typename real>
+__global__ void __launch_bounds__(256) fma_chain_kernel(real* out, int iters, real a, real b) {
+  real x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = real(threadIdx.x + k) * real(1e-3);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = fma_t<real>(x[k], a, b);
+  }
+  real s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == real(123.456)) out[0] = s;  // keep the chain alive
+}
+
+cudaError_t measure_fma_peak(bool fp64, int iters, double* tflops, double* ms_out) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  void* out = nullptr;
+  e = cudaMalloc(&out, 64);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  const int blocks = sms * 8, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0, 0);
+    if (fp64)
+      fma_chain_kernel<double><<<blocks, threads>>>((double*)out, iters, 0.999999, 1e-7);
+    else
+      fma_chain_kernel<float><<<blocks, threads>>>((float*)out, iters, 0.999999f, 1e-7f);
+    cudaEventRecord(t1, 0);
+    e = cudaEventSynchronize(t1);
+    if (e != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(out);
+  if (e != cudaSuccess) return e;
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+  *ms_out = best;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return cudaGetLastError();
+}
+
+}  // namespace acro

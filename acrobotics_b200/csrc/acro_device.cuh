@@ -1,0 +1,208 @@
+// acro_device.cuh - device-side data layout and math shared by every kernel of
+// libacro_b200 (sm_100a).  Internal; the public C ABI is include/acro_b200.h.
+//
+// Design notes:
+//  * one thread = one joint configuration; the 3x4 running transform lives in
+//    registers, the DH chain is unrolled at compile time (template NDOF);
+//  * the robot descriptor travels as a __grid_constant__ kernel parameter, so it
+//    sits in the constant bank, is read with warp-uniform LDC, and needs no
+//    global mutable state (handles are immutable => thread safe);
+//  * scene boxes are staged once per CTA into shared memory (uniform broadcast
+//    reads in the cull loop, per-lane reads in the SAT loop).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/acro_b200.h"
+
+namespace acro {
+
+constexpr int kMaxDof = ACRO_MAX_DOF;
+constexpr int kMaxBoxes = ACRO_MAX_ROBOT_BOXES;
+constexpr int kMaxPairs = ACRO_MAX_SELF_PAIRS;
+constexpr int kMaxScene = ACRO_MAX_SCENE_BOXES;
+constexpr int kMaxSaved = 16;    // robot boxes that are the earlier member of a self pair
+constexpr int kSceneStride = 20; // reals per scene box in the packed layout
+
+// ---------------------------------------------------------------------------
+// packed descriptors
+// ---------------------------------------------------------------------------
+template <typename real>
+struct BoxDev {
+  real half[3];
+  real radius;   // |half|: bounding-sphere radius
+  real off[12];  // 3x4 offset in the carrier frame
+  int32_t save_slot;     // >= 0: world pose is kept for later self pairs
+  int32_t rot_identity;  // offset is a pure translation
+};
+
+template <typename real>
+struct RobotDev {
+  int32_t ndof;
+  int32_t prismatic_mask;
+  int32_t has_tool_tip;
+  int32_t check_self;
+  int32_t n_boxes;
+  int32_t base_identity;
+  // boxes are sorted by processing order: slot 0 = base boxes, slots 1..ndof =
+  // link boxes, slot ndof+1 = tool boxes (carried by the last link frame)
+  int32_t slot_begin[kMaxDof + 3];
+  real a[kMaxDof], d[kMaxDof], theta[kMaxDof], ca[kMaxDof], sa[kMaxDof];
+  real base[12];
+  real tip[12];
+  BoxDev<real> boxes[kMaxBoxes];
+  // self pairs, grouped by their LATER box: partners of box b are
+  // partner[pair_begin[b] .. pair_begin[b+1]) and hold the earlier box index
+  uint8_t pair_begin[kMaxBoxes + 1];
+  uint8_t partner[kMaxPairs];
+};
+
+// Scene box, packed as kSceneStride reals:
+//  [0..8] R2 row-major, [9..11] T2, [12..14] half extents B, [15] radius,
+//  [16] max half extent, [17..19] unused
+template <typename real>
+struct SceneView {
+  const real* boxes;  // device pointer, n * kSceneStride
+  int32_t n;
+};
+
+// ---------------------------------------------------------------------------
+// small math helpers
+// ---------------------------------------------------------------------------
+template <typename real>
+__device__ __forceinline__ void sincos_t(real x, real* s, real* c);
+template <>
+__device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) {
+  sincos(x, s, c);
+}
+template <>
+__device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) {
+  sincosf(x, s, c);
+}
+
+template <typename real>
+__device__ __forceinline__ real fma_t(real a, real b, real c);
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) {
+  return fma(a, b, c);
+}
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) {
+  return fmaf(a, b, c);
+}
+
+template <typename real>
+__device__ __forceinline__ real abs_t(real x) {
+  return x < real(0) ? -x : x;
+}
+template <>
+__device__ __forceinline__ double abs_t<double>(double x) {
+  return fabs(x);
+}
+template <>
+__device__ __forceinline__ float abs_t<float>(float x) {
+  return fabsf(x);
+}
+
+template <typename real>
+struct Eps;
+template <>
+struct Eps<double> {
+  static constexpr double v = 2.220446049250313e-16;
+};
+template <>
+struct Eps<float> {
+  static constexpr float v = 1.1920929e-07f;
+};
+
+// 3x4 rigid transform in registers: R row-major + p
+template <typename real>
+struct Tf {
+  real r[9];
+  real p[3];
+};
+
+template <typename real>
+__device__ __forceinline__ void tf_load(Tf<real>& T, const real* m) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    T.r[3 * r + 0] = m[4 * r + 0];
+    T.r[3 * r + 1] = m[4 * r + 1];
+    T.r[3 * r + 2] = m[4 * r + 2];
+    T.p[r] = m[4 * r + 3];
+  }
+}
+
+// T <- T * DH(ct, st, ca, sa, a, d)      (reference link.py:35-58, robot.py:64-66)
+// Factored form: u = R[:,0]ct + R[:,1]st ; w = R[:,1]ct - R[:,0]st ;
+//   col0 = u ; col1 = w ca + R[:,2] sa ; col2 = R[:,2] ca - w sa ;
+//   p += a u + d R[:,2]          (30 FMA-class instructions per joint)
+template <typename real>
+__device__ __forceinline__ void tf_mul_dh(Tf<real>& T, real ct, real st, real ca, real sa, real a,
+                                          real d) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const real r0 = T.r[3 * r + 0], r1 = T.r[3 * r + 1], r2 = T.r[3 * r + 2];
+    const real u = fma_t(r1, st, r0 * ct);
+    const real w = fma_t(r1, ct, -(r0 * st));
+    T.r[3 * r + 0] = u;
+    T.r[3 * r + 1] = fma_t(r2, sa, w * ca);
+    T.r[3 * r + 2] = fma_t(r2, ca, -(w * sa));
+    T.p[r] = fma_t(d, r2, fma_t(a, u, T.p[r]));
+  }
+}
+
+// out = T * M  (M is a 3x4 constant from the descriptor)
+template <typename real>
+__device__ __forceinline__ void tf_mul(Tf<real>& out, const Tf<real>& T, const real* m) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const real r0 = T.r[3 * r + 0], r1 = T.r[3 * r + 1], r2 = T.r[3 * r + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      out.r[3 * r + c] = fma_t(r2, m[8 + c], fma_t(r1, m[4 + c], r0 * m[c]));
+    out.p[r] = fma_t(r2, m[11], fma_t(r1, m[7], fma_t(r0, m[3], T.p[r])));
+  }
+}
+
+// joint i of the chain: revolute theta = q, prismatic d = q   (link.py:40-44)
+template <typename real>
+__device__ __forceinline__ void chain_step(Tf<real>& T, const RobotDev<real>& rb, int i, real qi) {
+  real th, dd;
+  if ((rb.prismatic_mask >> i) & 1) {
+    th = rb.theta[i];
+    dd = qi;
+  } else {
+    th = qi;
+    dd = rb.d[i];
+  }
+  real s, c;
+  sincos_t<real>(th, &s, &c);
+  tf_mul_dh<real>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], dd);
+}
+
+// ---------------------------------------------------------------------------
+// coalesced row access: a CTA moves `rows` consecutive rows of `W` reals between
+// global memory and shared memory as one flat, fully coalesced block.
+// ---------------------------------------------------------------------------
+template <typename real>
+__device__ __forceinline__ void cta_load_rows(real* smem, const real* __restrict__ g,
+                                              int64_t row0, int64_t n_rows_total, int rows,
+                                              int W) {
+  const int64_t base = row0 * W;
+  int64_t avail = (n_rows_total - row0) * (int64_t)W;
+  const int count = (int)(avail < (int64_t)rows * W ? (avail < 0 ? 0 : avail) : (int64_t)rows * W);
+  for (int k = threadIdx.x; k < count; k += blockDim.x) smem[k] = g[base + k];
+}
+
+template <typename real>
+__device__ __forceinline__ void cta_store_rows(real* __restrict__ g, const real* smem,
+                                               int64_t row0, int64_t n_rows_total, int rows,
+                                               int W) {
+  const int64_t base = row0 * W;
+  int64_t avail = (n_rows_total - row0) * (int64_t)W;
+  const int count = (int)(avail < (int64_t)rows * W ? (avail < 0 ? 0 : avail) : (int64_t)rows * W);
+  for (int k = threadIdx.x; k < count; k += blockDim.x) g[base + k] = smem[k];
+}
+
+}  // namespace acro

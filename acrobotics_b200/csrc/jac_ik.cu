@@ -1,0 +1,505 @@
+// jac_ik.cu - K3/K4 geometric Jacobians and K5 analytical inverse kinematics.
+//
+// Jacobians replace the casadi AD functions of reference
+// src/acrobotics/robot.py:157-171 (fk_casadi :129-136, fk_rpy_casadi :138-144).
+// IK replaces Kuka.ik (src/acrobotics/robot_examples.py:188-218), arm_2.ik
+// (inverse_kinematics/arm_2.py:5-104), spherical_wrist.ik
+// (inverse_kinematics/spherical_wrist.py:5-30) and anthropomorphic_arm.ik
+// (inverse_kinematics/anthropomorphic_arm.py:5-55).
+//
+// All HBM bound: rows are staged through shared memory so that global traffic
+// is flat and coalesced.
+#include <math_constants.h>
+
+#include "acro_collide.cuh"
+#include "acro_launch.h"
+
+namespace acro {
+
+// flat coalesced copy of `W` reals per configuration from padded smem rows
+template <int W>
+__device__ __forceinline__ void flush_rows(double* __restrict__ out, const double* s_rows,
+                                           int64_t row0, int64_t n) {
+  constexpr int WP = W | 1;
+  const int64_t left = n - row0;
+  const int rows = left < kTile ? (int)left : kTile;
+  for (int k = threadIdx.x; k < rows * W; k += blockDim.x) {
+    const int r = k / W, c = k - r * W;
+    out[(row0 + r) * W + c] = s_rows[r * WP + c];
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void fetch_rows(double* s_rows, const double* __restrict__ in,
+                                           int64_t row0, int64_t n) {
+  constexpr int WP = W | 1;
+  const int64_t left = n - row0;
+  const int rows = left < kTile ? (int)left : kTile;
+  for (int k = threadIdx.x; k < rows * W; k += blockDim.x) {
+    const int r = k / W, c = k - r * W;
+    s_rows[r * WP + c] = in[(row0 + r) * W + c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Jacobians
+// ---------------------------------------------------------------------------
+template <int NDOF, bool RPY>
+__global__ void __launch_bounds__(kTile)
+    jac_kernel(const __grid_constant__ RobotDev<double> rb, const double* __restrict__ q,
+               int64_t n, int layout, double* __restrict__ J) {
+  constexpr int ROWS = RPY ? 6 : 3;
+  constexpr int W = ROWS * NDOF;
+  constexpr int WP = W | 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_q = reinterpret_cast<double*>(smem_raw);
+  double* s_out = s_q + kTile * NDOF;
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  double qv[NDOF];
+  load_q<double, NDOF>(qv, s_q, q, row0, n, layout);
+
+  // joint axis z_{i-1} and origin o_{i-1} are read off the frame *before* link i
+  double z[NDOF][3], o[NDOF][3];
+  Tf<double> T;
+  tf_load<double>(T, rb.base);
+#pragma unroll
+  for (int i = 0; i < NDOF; ++i) {
+    z[i][0] = T.r[2]; z[i][1] = T.r[5]; z[i][2] = T.r[8];
+    o[i][0] = T.p[0]; o[i][1] = T.p[1]; o[i][2] = T.p[2];
+    chain_step<double>(T, rb, i, qv[i]);
+  }
+  if (rb.has_tool_tip) {
+    Tf<double> E;
+    tf_mul<double>(E, T, rb.tip);
+    T = E;
+  }
+  double* row = s_out + threadIdx.x * WP;
+  // angle terms of robot.py:138-144, differentiated by the chain rule
+  const double T00 = T.r[0], T01 = T.r[1], T02 = T.r[2], T12 = T.r[5], T22 = T.r[8];
+  const double s = sqrt(T00 * T00 + T01 * T01);
+  const double inv_x = 1.0 / (T22 * T22 + T12 * T12);  // r_x = atan2(-T12, T22)
+  const double inv_y = 1.0 / (s * s + T02 * T02);      // r_y = atan2( T02, s)
+  const double inv_z = 1.0 / (T22 * T22 + T01 * T01);  // r_z = atan2(-T01, T22)
+#pragma unroll
+  for (int i = 0; i < NDOF; ++i) {
+    const bool prismatic = (rb.prismatic_mask >> i) & 1;
+    const double z0 = z[i][0], z1 = z[i][1], z2 = z[i][2];
+    if (prismatic) {
+      row[0 * NDOF + i] = z0;
+      row[1 * NDOF + i] = z1;
+      row[2 * NDOF + i] = z2;
+      if (RPY) {
+        row[3 * NDOF + i] = 0.0;
+        row[4 * NDOF + i] = 0.0;
+        row[5 * NDOF + i] = 0.0;
+      }
+    } else {
+      const double r0 = T.p[0] - o[i][0], r1 = T.p[1] - o[i][1], r2 = T.p[2] - o[i][2];
+      row[0 * NDOF + i] = z1 * r2 - z2 * r1;
+      row[1 * NDOF + i] = z2 * r0 - z0 * r2;
+      row[2 * NDOF + i] = z0 * r1 - z1 * r0;
+      if (RPY) {
+        // dR = [z]x R : only the five entries the angle formulas touch
+        const double d00 = z1 * T.r[6] - z2 * T.r[3];
+        const double d01 = z1 * T.r[7] - z2 * T.r[4];
+        const double d02 = z1 * T.r[8] - z2 * T.r[5];
+        const double d12 = z2 * T.r[2] - z0 * T.r[8];
+        const double d22 = z0 * T.r[5] - z1 * T.r[2];
+        const double ds = (T00 * d00 + T01 * d01) / s;
+        // d atan2(y, x) = (x dy - y dx) / (x^2 + y^2)
+        row[3 * NDOF + i] = (T22 * (-d12) - (-T12) * d22) * inv_x;
+        row[4 * NDOF + i] = (s * d02 - T02 * ds) * inv_y;
+        row[5 * NDOF + i] = (T22 * (-d01) - (-T01) * d22) * inv_z;
+      }
+    }
+  }
+  __syncthreads();
+  flush_rows<W>(J, s_out, row0, n);
+}
+
+cudaError_t launch_jac(const RobotDev<double>& rb, const double* q, int64_t n, int layout,
+                       double* J, bool rpy, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  ACRO_DISPATCH_NDOF(rb.ndof, {
+    if (rpy) {
+      const size_t smem = sizeof(double) * (kTile * NDOF + kTile * ((6 * NDOF) | 1));
+      auto k = jac_kernel<NDOF, true>;
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, J);
+    } else {
+      const size_t smem = sizeof(double) * (kTile * NDOF + kTile * ((3 * NDOF) | 1));
+      jac_kernel<NDOF, false><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, J);
+    }
+  });
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// analytical IK building blocks
+// ---------------------------------------------------------------------------
+struct Arm2Sol {
+  double q[4][3];  // [pos_a, pos_b, neg_a, neg_b] x (q1, q2, q3)
+  bool pos, neg;
+};
+
+// reach test + snap of arm_2.py:37-45; returns false when unreachable
+__device__ __forceinline__ bool c3_branch(double& c3, double& s3) {
+  const double tol = 1e-6;
+  if (c3 > (1 + tol) || c3 < -(1 + tol)) return false;
+  if (c3 > (1 - tol) || c3 < -(1 - tol)) c3 = c3 > 0 ? 1.0 : -1.0;  // np.sign
+  s3 = sqrt(1 - c3 * c3);
+  return true;
+}
+
+// inverse_kinematics/arm_2.py:5-104
+__device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1, double a2,
+                                        double a3, Arm2Sol& S) {
+  const double nan = CUDART_NAN;
+  const double q1_pos = atan2(y, x);
+  const double q1_neg = atan2(-y, -x);
+  const double den = 2 * a2 * a3;
+  const double num = a1 * a1 - a2 * a2 - a3 * a3 + x * x + y * y + z * z;
+  const double L = sqrt(x * x + y * y);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) S.q[k][0] = S.q[k][1] = S.q[k][2] = nan;
+
+  double s1, c1, c3, s3 = 0;
+  sincos(q1_pos, &s1, &c1);
+  c3 = (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
+  S.pos = c3_branch(c3, s3);
+  if (S.pos) {
+    const double q3a = atan2(s3, c3), q3b = atan2(-s3, c3);
+    const double cc = cos(q3b), ss = sin(q3a);  // sic: arm_2.py:65
+    S.q[0][0] = q1_pos;
+    S.q[0][1] = atan2(-a3 * ss * (L - a1) + z * (a2 + a3 * cc),
+                      a3 * ss * z + (L - a1) * (a2 + a3 * cc));
+    S.q[0][2] = q3a;
+    S.q[1][0] = q1_pos;
+    S.q[1][1] = atan2(a3 * ss * (L - a1) + z * (a2 + a3 * cc),
+                      -a3 * ss * z + (L - a1) * (a2 + a3 * cc));
+    S.q[1][2] = q3b;
+  }
+  sincos(q1_neg, &s1, &c1);
+  c3 = (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
+  S.neg = c3_branch(c3, s3);
+  if (S.neg) {
+    const double q3a = atan2(s3, c3), q3b = atan2(-s3, c3);
+    const double ss = sin(q3a), cc = cos(q3b);  // arm_2.py:76-77
+    S.q[2][0] = q1_neg;
+    S.q[2][1] = atan2(a3 * ss * (L + a1) + z * (a2 + a3 * cc),
+                      a3 * ss * z - (L + a1) * (a2 + a3 * cc));
+    S.q[2][2] = q3a;
+    S.q[3][0] = q1_neg;
+    S.q[3][1] = atan2(-a3 * ss * (L + a1) + z * (a2 + a3 * cc),
+                      -a3 * ss * z - (L + a1) * (a2 + a3 * cc));
+    S.q[3][2] = q3b;
+  }
+}
+
+// inverse_kinematics/spherical_wrist.py:5-30; Rb, R row-major 3x3
+__device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, double* sol1,
+                                         double* sol2) {
+  // Rrel = Rb^T R ; a = Rrel[:,2], s_z = Rrel[2,1], n_z = Rrel[2,0]
+  const double a0 = Rb[0] * R[2] + Rb[3] * R[5] + Rb[6] * R[8];
+  const double a1 = Rb[1] * R[2] + Rb[4] * R[5] + Rb[7] * R[8];
+  const double a2 = Rb[2] * R[2] + Rb[5] * R[5] + Rb[8] * R[8];
+  const double sz = Rb[2] * R[1] + Rb[5] * R[4] + Rb[8] * R[7];
+  const double nz = Rb[2] * R[0] + Rb[5] * R[3] + Rb[8] * R[6];
+  const double A = sqrt(a0 * a0 + a1 * a1);
+  sol1[0] = atan2(a1, a0);
+  sol1[1] = atan2(A, a2);
+  sol1[2] = atan2(sz, -nz);
+  sol2[0] = atan2(-a1, -a0);
+  sol2[1] = atan2(-A, a2);
+  sol2[2] = atan2(-sz, nz);
+}
+
+// Kuka.ik for one pose (robot_examples.py:188-218).  T: 16 doubles row-major.
+// sol[slot][6], returns the validity bit set (slot = 2*arm + wrist).
+__device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const double* Tin,
+                                            double sol[8][6]) {
+  Tf<double> Tw;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Tw.r[3 * r] = Tin[4 * r];
+    Tw.r[3 * r + 1] = Tin[4 * r + 1];
+    Tw.r[3 * r + 2] = Tin[4 * r + 2];
+    Tw.p[r] = Tin[4 * r + 3];
+  }
+  if (!rb.base_identity) {  // Tw = tf_inverse(tf_base) @ T   (:190-191, :14-23)
+    Tf<double> X;
+    const double* b = rb.base;
+    const double dx = Tw.p[0] - b[3], dy = Tw.p[1] - b[7], dz = Tw.p[2] - b[11];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        X.r[3 * i + j] = b[i] * Tw.r[j] + b[4 + i] * Tw.r[3 + j] + b[8 + i] * Tw.r[6 + j];
+      X.p[i] = b[i] * dx + b[4 + i] * dy + b[8 + i] * dz;
+    }
+    Tw = X;
+  }
+  if (rb.has_tool_tip) {  // Tw = Tw @ tf_inverse(tf_tool_tip)   (:193-194)
+    Tf<double> X;
+    const double* t = rb.tip;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)  // R' = R * Rt^T
+        X.r[3 * i + j] = Tw.r[3 * i] * t[4 * j] + Tw.r[3 * i + 1] * t[4 * j + 1] +
+                         Tw.r[3 * i + 2] * t[4 * j + 2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      X.p[i] = Tw.p[i] - (X.r[3 * i] * t[3] + X.r[3 * i + 1] * t[7] + X.r[3 * i + 2] * t[11]);
+    Tw = X;
+  }
+  const double a1 = rb.a[0], a2 = rb.a[1], d4 = rb.d[3], d6 = rb.d[5];
+  // wrist centre (:196-199)
+  const double px = Tw.p[0] - Tw.r[2] * d6;
+  const double py = Tw.p[1] - Tw.r[5] * d6;
+  const double pz = Tw.p[2] - Tw.r[8] * d6;
+  Arm2Sol S;
+  arm2_ik(px, py, pz, a1, a2, d4, S);
+  const double nan = CUDART_NAN;
+  const double half_pi_cos = 6.123233995736766e-17;  // np.cos(np.pi / 2)
+  unsigned valid = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool ok = (k < 2) ? S.pos : S.neg;
+    if (ok) {
+      const double q1 = S.q[k][0], q2 = S.q[k][1], q3 = S.q[k][2] + CUDART_PI / 2;  // :204
+      // orientation of Arm2(a1, a2, a3=d4).fk(q_arm)   (:207, robot_examples.py:114-131)
+      Tf<double> F;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) F.r[e] = (e % 4 == 0) ? 1.0 : 0.0;
+      F.p[0] = F.p[1] = F.p[2] = 0.0;
+      double s, c;
+      sincos(q1, &s, &c);
+      tf_mul_dh<double>(F, c, s, half_pi_cos, 1.0, a1, 0.0);
+      sincos(q2, &s, &c);
+      tf_mul_dh<double>(F, c, s, 1.0, 0.0, a2, 0.0);
+      sincos(q3, &s, &c);
+      tf_mul_dh<double>(F, c, s, half_pi_cos, 1.0, d4, 0.0);
+      double w1[3], w2[3];
+      wrist_ik(F.r, Tw.r, w1, w2);
+      sol[2 * k][0] = q1; sol[2 * k][1] = q2; sol[2 * k][2] = q3;
+      sol[2 * k][3] = w1[0]; sol[2 * k][4] = w1[1]; sol[2 * k][5] = w1[2];
+      sol[2 * k + 1][0] = q1; sol[2 * k + 1][1] = q2; sol[2 * k + 1][2] = q3;
+      sol[2 * k + 1][3] = w2[0]; sol[2 * k + 1][4] = w2[1]; sol[2 * k + 1][5] = w2[2];
+      valid |= 3u << (2 * k);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) sol[2 * k][e] = sol[2 * k + 1][e] = nan;
+    }
+  }
+  return valid;
+}
+
+template <bool WITH_CC>
+__global__ void __launch_bounds__(kTile)
+    ik_kuka_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
+                   const double* __restrict__ T, int64_t n, double* __restrict__ q_out,
+                   uint8_t* __restrict__ valid, uint8_t* __restrict__ free_mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_rows = reinterpret_cast<double*>(smem_raw);  // 128 x 49 doubles
+  double* s_scene = s_rows + kTile * 49;
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
+  if (WITH_CC)
+    for (int k = threadIdx.x; k < sc.n * kSceneStride; k += blockDim.x) s_scene[k] = sc.boxes[k];
+  fetch_rows<16>(s_rows, T, row0, n);
+  __syncthreads();
+  double Tin[16];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) Tin[k] = idx < n ? s_rows[threadIdx.x * 17 + k] : (k % 5 == 0);
+  __syncthreads();
+  double sol[8][6];
+  const unsigned vbits = kuka_ik(rb, Tin, sol);
+  double* row = s_rows + threadIdx.x * 49;
+#pragma unroll
+  for (int sl = 0; sl < 8; ++sl)
+#pragma unroll
+    for (int e = 0; e < 6; ++e) row[sl * 6 + e] = sol[sl][e];
+  __syncthreads();
+  flush_rows<48>(q_out, s_rows, row0, n);
+  if (idx < n) valid[idx] = (uint8_t)vbits;
+  if (WITH_CC) {
+    unsigned freebits = 0;
+    for (int sl = 0; sl < 8; ++sl) {  // path/path_pt_base.py:107-109
+      const bool act = idx < n && ((vbits >> sl) & 1);
+      double qv[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) qv[e] = act ? sol[sl][e] : 0.0;
+      Verdict<double, false> v;
+      config_collision<double, 6, false>(rb, qv, s_scene, sc.n, 0.0, act, v);
+      if (act && !v.hit) freebits |= 1u << sl;
+    }
+    if (idx < n) free_mask[idx] = (uint8_t)freebits;
+  }
+}
+
+cudaError_t launch_ik_kuka(const RobotDev<double>& rb, const double* T, int64_t n, double* q_out,
+                           uint8_t* valid, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(double) * kTile * 49;
+  auto k = ik_kuka_kernel<false>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<(unsigned)tiles, kTile, smem, st>>>(rb, SceneView<double>{nullptr, 0}, T, n, q_out, valid,
+                                          nullptr);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ik_kuka_cc(const RobotDev<double>& rb, SceneView<double> sc, const double* T,
+                              int64_t n, double* q_out, uint8_t* valid, uint8_t* free_mask,
+                              cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(double) * (kTile * 49 + sc.n * kSceneStride);
+  auto k = ik_kuka_kernel<true>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<(unsigned)tiles, kTile, smem, st>>>(rb, sc, T, n, q_out, valid, free_mask);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone arm / wrist IK
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile)
+    ik_arm2_kernel(double a1, double a2, double a3, const double* __restrict__ p, int64_t n,
+                   double* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  __shared__ double s_rows[kTile * 13];
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
+  fetch_rows<3>(s_rows, p, row0, n);
+  __syncthreads();
+  const double x = idx < n ? s_rows[threadIdx.x * 3] : 1.0;
+  const double y = idx < n ? s_rows[threadIdx.x * 3 + 1] : 0.0;
+  const double z = idx < n ? s_rows[threadIdx.x * 3 + 2] : 0.0;
+  __syncthreads();
+  Arm2Sol S;
+  arm2_ik(x, y, z, a1, a2, a3, S);
+  double* row = s_rows + threadIdx.x * 13;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int e = 0; e < 3; ++e) row[3 * k + e] = S.q[k][e];
+  __syncthreads();
+  flush_rows<12>(q_out, s_rows, row0, n);
+  if (idx < n) valid[idx] = (uint8_t)((S.pos ? 3u : 0u) | (S.neg ? 12u : 0u));
+}
+
+// inverse_kinematics/anthropomorphic_arm.py:5-55
+__global__ void __launch_bounds__(kTile)
+    ik_anthro_kernel(double l2, double l3, const double* __restrict__ p, int64_t n,
+                     double* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  __shared__ double s_rows[kTile * 13];
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
+  fetch_rows<3>(s_rows, p, row0, n);
+  __syncthreads();
+  const double px = idx < n ? s_rows[threadIdx.x * 3] : 1.0;
+  const double py = idx < n ? s_rows[threadIdx.x * 3 + 1] : 0.0;
+  const double pz = idx < n ? s_rows[threadIdx.x * 3 + 2] : 0.0;
+  __syncthreads();
+  const double nan = CUDART_NAN;
+  double sol[4][3];
+  const double Lps = px * px + py * py + pz * pz;
+  double c3 = (Lps - l2 * l2 - l3 * l3) / (2 * l2 * l3), s3 = 0;
+  const bool ok = c3_branch(c3, s3);
+  if (ok) {
+    const double t3_1 = atan2(s3, c3), t3_2 = atan2(-s3, c3);
+    const double Lxy = sqrt(px * px + py * py);
+    const double A = l2 + l3 * c3, B = l3 * s3;
+    const double t2_1 = atan2(pz * A - Lxy * B, Lxy * A + pz * B);
+    const double t2_2 = atan2(pz * A + Lxy * B, -Lxy * A + pz * B);
+    const double t2_3 = atan2(pz * A + Lxy * B, Lxy * A - pz * B);
+    const double t2_4 = atan2(pz * A - Lxy * B, -Lxy * A - pz * B);
+    const double t1_1 = atan2(py, px), t1_2 = atan2(-py, -px);
+    sol[0][0] = t1_1; sol[0][1] = t2_1; sol[0][2] = t3_1;
+    sol[1][0] = t1_1; sol[1][1] = t2_3; sol[1][2] = t3_2;
+    sol[2][0] = t1_2; sol[2][1] = t2_2; sol[2][2] = t3_1;
+    sol[3][0] = t1_2; sol[3][1] = t2_4; sol[3][2] = t3_2;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sol[k][0] = sol[k][1] = sol[k][2] = nan;
+  }
+  double* row = s_rows + threadIdx.x * 13;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int e = 0; e < 3; ++e) row[3 * k + e] = sol[k][e];
+  __syncthreads();
+  flush_rows<12>(q_out, s_rows, row0, n);
+  if (idx < n) valid[idx] = ok ? 0xF : 0;
+}
+
+struct Mat3 {
+  double m[9];
+};
+
+__global__ void __launch_bounds__(kTile)
+    ik_wrist_kernel(const double* __restrict__ R, Mat3 Rb, int64_t n, double* __restrict__ q_out) {
+  __shared__ double s_rows[kTile * 9];
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
+  fetch_rows<9>(s_rows, R, row0, n);
+  __syncthreads();
+  double Rm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rm[k] = idx < n ? s_rows[threadIdx.x * 9 + k] : (k % 4 == 0);
+  __syncthreads();
+  double w1[3], w2[3];
+  wrist_ik(Rb.m, Rm, w1, w2);
+  double* row = s_rows + threadIdx.x * 7;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    row[e] = w1[e];
+    row[3 + e] = w2[e];
+  }
+  __syncthreads();
+  flush_rows<6>(q_out, s_rows, row0, n);
+}
+
+cudaError_t launch_ik_arm2(double a1, double a2, double a3, const double* p, int64_t n,
+                           double* q_out, uint8_t* valid, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  ik_arm2_kernel<<<(unsigned)tiles, kTile, 0, st>>>(a1, a2, a3, p, n, q_out, valid);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ik_anthro(double l2, double l3, const double* p, int64_t n, double* q_out,
+                             uint8_t* valid, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  ik_anthro_kernel<<<(unsigned)tiles, kTile, 0, st>>>(l2, l3, p, n, q_out, valid);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ik_wrist(const double* R, const double* Rb9, int64_t n, double* q_out,
+                            cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  Mat3 Rb;
+  for (int k = 0; k < 9; ++k) Rb.m[k] = Rb9[k];
+  ik_wrist_kernel<<<(unsigned)tiles, kTile, 0, st>>>(R, Rb, n, q_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace acro

@@ -1,0 +1,194 @@
+/*
+ * acro_b200.h - C ABI of libacro_b200.so: the B200 (sm_100a) implementation of
+ * the acrobotics forward-kinematics + collision-checking hot path.
+ *
+ * The reference (JeroenDM/acrobotics, pure Python) has no FFI layer of its own
+ * for this path: the seam is a set of Python methods plus one native call,
+ *   fcl.collide(o1, o2, request, result)          src/acrobotics/shapes.py:52-58
+ * Each entry point below names the reference interface it replaces.  A
+ * maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every array is a raw pointer + sizes;
+ *   - 4x4 homogeneous transforms travel as 12 doubles, row-major 3x4 (the
+ *     bottom row [0 0 0 1] is implicit);
+ *   - "device" entry points take DEVICE pointers and are asynchronous on the
+ *     given CUDA stream (a cudaStream_t passed as void*, NULL = default stream);
+ *     "_host" entry points take HOST pointers, run a chunked, double-buffered
+ *     H2D -> kernel -> D2H pipeline on library-owned streams and return after
+ *     the results are in the host buffer;
+ *   - the caller owns every buffer; the library owns only the opaque handles;
+ *     handles are immutable after creation, so calls are thread-safe given
+ *     distinct output buffers;
+ *   - return value: 0 = OK, negative = ACRO_E_* library error, positive =
+ *     cudaError_t.  Nothing is thrown across the boundary; acro_last_error()
+ *     returns a thread-local message.
+ *   - collision masks are bit sets: word i/32, bit i%32 = configuration i,
+ *     ceil(N/32) uint32 words, tail bits zero.
+ */
+#ifndef ACRO_B200_H
+#define ACRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACRO_ABI_VERSION 1
+
+#define ACRO_MAX_DOF 8
+#define ACRO_MAX_ROBOT_BOXES 24
+#define ACRO_MAX_SELF_PAIRS 160
+#define ACRO_MAX_SCENE_BOXES 64
+
+#define ACRO_E_INVALID (-1)     /* bad argument                                  */
+#define ACRO_E_UNSUPPORTED (-2) /* e.g. ndof or box count above the compiled caps */
+#define ACRO_E_NOGPU (-3)       /* no usable CUDA device                          */
+
+/* carrier codes for AcroRobotBox.carrier */
+#define ACRO_CARRIER_BASE (-1) /* rides on tf_base          (robot.py:257-260)  */
+#define ACRO_CARRIER_TOOL (-2) /* rides on last link frame  (robot.py:251-254)  */
+
+/* q layouts */
+#define ACRO_Q_AOS 0 /* (N, ndof) row-major: the reference's natural layout      */
+#define ACRO_Q_SOA 1 /* (ndof, N): joint-major, fully coalesced                  */
+
+/* One oriented box: reference Box(dx,dy,dz) (shapes.py:105-114) + its 4x4 tf.   */
+typedef struct AcroBox {
+  double half[3]; /* dx/2, dy/2, dz/2 */
+  double tf[12];  /* row-major 3x4    */
+} AcroBox;
+
+/* A collision box of the robot: link.geometry / geometry_tool / geometry_base
+ * entries (link.py:80-83, robot.py:178-179, :197-204).                          */
+typedef struct AcroRobotBox {
+  int32_t carrier; /* link index 0..ndof-1, ACRO_CARRIER_BASE or ACRO_CARRIER_TOOL */
+  int32_t reserved;
+  double half[3];
+  double tf[12]; /* offset of the box in its carrier frame */
+} AcroRobotBox;
+
+/* Flattened Robot (robot.py:36-57, :174-195) + DH table (link.py:8, :35-58).    */
+typedef struct AcroRobotDesc {
+  int32_t ndof;
+  int32_t joint_type[ACRO_MAX_DOF]; /* 0 revolute ('r'), 1 prismatic ('p') (link.py:11-13) */
+  double a[ACRO_MAX_DOF];
+  double d[ACRO_MAX_DOF];
+  double theta[ACRO_MAX_DOF];
+  /* cos/sin of the DH alpha, computed on the host exactly as the reference does
+   * (np.cos(alpha), link.py:48-49: cos(pi/2) is 6.1e-17, not 0).                */
+  double cos_alpha[ACRO_MAX_DOF];
+  double sin_alpha[ACRO_MAX_DOF];
+  double tf_base[12];     /* robot.py:55 */
+  int32_t has_tool_tip;   /* robot.py:57 (None -> 0) */
+  int32_t check_self;     /* robot.py:182 do_check_self_collision */
+  double tf_tool_tip[12]; /* relative to the last link */
+  int32_t n_boxes;
+  int32_t n_self_pairs;
+  AcroRobotBox boxes[ACRO_MAX_ROBOT_BOXES];
+  /* unordered pairs of indices into boxes[] that the self-collision test visits
+   * (collision_matrix band robot.py:185-186, :206-211; tool vs links :214-220)  */
+  int32_t self_pairs[ACRO_MAX_SELF_PAIRS][2];
+} AcroRobotDesc;
+
+typedef struct AcroRobot AcroRobot; /* opaque */
+typedef struct AcroScene AcroScene; /* opaque */
+
+int acro_abi_version(void);
+const char* acro_last_error(void);
+/* number of CUDA devices visible, <0 on error; never initialises a context */
+int acro_device_count(void);
+
+/* Robot(links, joint_limits) + geometry  ->  immutable device descriptor.
+ * Replaces the per-call Python object walk in robot.py:244-273.                  */
+int acro_robot_create(const AcroRobotDesc* desc, AcroRobot** out);
+void acro_robot_destroy(AcroRobot* robot);
+
+/* Scene(shapes, tf_shapes) (geometry.py:12-14), boxes only.  n may be 0.         */
+int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out);
+void acro_scene_destroy(AcroScene* scene);
+
+/* ---- the fcl.collide seam -------------------------------------------------------
+ * n independent Box-Box tests: a[i] against b[i] (each an AcroBox with its WORLD
+ * transform), FCL boxBox2 semantics (touching = colliding).  Replaces
+ * Shape.is_in_collision -> fcl.collide (shapes.py:50-58), the one native call on
+ * the reference's path.  mask bit i = pair i collides.  Device pointers.         */
+int acro_collide_boxes_f64(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,
+                           void* stream);
+
+/* ---- K1: forward kinematics ------------------------------------------------
+ * Robot.fk (robot.py:59-69) when all_links == 0: T_out is (N,4,4) row-major,
+ * tool tip applied.  Robot.fk_all_links (robot.py:82-91) when all_links != 0:
+ * T_out is (N,ndof,4,4), base applied, tool tip not.                           */
+int acro_fk_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                double* T_out, int32_t all_links, void* stream);
+int acro_fk_f32(const AcroRobot* robot, const float* q, int64_t n, int32_t q_layout,
+                float* T_out, int32_t all_links, void* stream);
+/* Robot.fk_rpy (robot.py:71-80): out (N,6) = [x,y,z,r_x,r_y,r_z].               */
+int acro_fk_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                    double* out, void* stream);
+
+/* ---- K2: fused FK -> collision ----------------------------------------------
+ * Robot.is_in_collision(q, scene) (robot.py:244-273) for N configurations:
+ * tool x scene, base x scene, link x scene, and (check_self) the self pairs,
+ * each box pair decided by FCL's boxBox2 separating-axis test (shapes.py:50-58).
+ * scene may be NULL (self collision only: Robot.is_in_self_collision,
+ * robot.py:239-242).  near_mask (nullable): bit set when the configuration's
+ * decisive SAT quantity is within +-margin of contact (reported separately).   */
+int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
+                   int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
+                   void* stream);
+int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
+                   int32_t q_layout, uint32_t* mask, void* stream);
+/* Same, HOST buffers: pipelined H2D/kernel/D2H inside the call.                 */
+int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
+                        int64_t n, uint32_t* mask_host, int64_t chunk);
+
+/* ---- K3/K4: Jacobians (robot.py:157-171; casadi AD in the reference) ----------
+ * J_out (N,3,ndof) / (N,6,ndof) row-major.  The descriptor's base / tool tip are
+ * used as given (the Python layer passes the as-constructed ones).              */
+int acro_jac_pos_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                     double* J_out, void* stream);
+int acro_jac_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,
+                     double* J_out, void* stream);
+
+/* ---- K5: analytical IK ---------------------------------------------------------
+ * Kuka.ik (robot_examples.py:188-218 = arm_2.py:5-104 + spherical_wrist.py:5-30).
+ * T (N,4,4) row-major -> q_out (N,8,6), slot = 2*arm_branch + wrist_branch in the
+ * reference's order; valid[i] bit s = slot s exists (invalid slots are NaN).    */
+int acro_ik_kuka_f64(const AcroRobot* robot, const double* T, int64_t n, double* q_out,
+                     uint8_t* valid, void* stream);
+/* arm_2.ik: p (N,3) -> q_out (N,4,3), valid bits [pos_a,pos_b,neg_a,neg_b].      */
+int acro_ik_arm2_f64(double a1, double a2, double a3, const double* p, int64_t n, double* q_out,
+                     uint8_t* valid, void* stream);
+/* anthropomorphic_arm.ik: p (N,3) -> q_out (N,4,3), valid[i] = 0 or 0xF.         */
+int acro_ik_anthropomorphic_f64(double l2, double l3, const double* p, int64_t n, double* q_out,
+                                uint8_t* valid, void* stream);
+/* spherical_wrist.ik: R (N,3,3), R_base (3,3) host -> q_out (N,2,3).             */
+int acro_ik_wrist_f64(const double* R, const double* R_base_host, int64_t n, double* q_out,
+                      void* stream);
+/* Fused IK -> collision filter (path/path_pt_base.py:76-85, :107-109):
+ * free_mask[i] bit s = slot s exists AND is collision free.                     */
+int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* T,
+                        int64_t n, double* q_out, uint8_t* valid, uint8_t* free_mask,
+                        void* stream);
+
+/* ---- K6: discretised path sweep -----------------------------------------------
+ * Robot.is_path_in_collision_discrete (robot.py:229-237, :275-283) for E
+ * segments: q_start/q_goal (E,ndof); mask bit e = some interpolant collides.    */
+int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
+                     const double* q_goal, int64_t n_segments, double max_q_step, uint32_t* mask,
+                     void* stream);
+
+/* ---- measurement helpers ----------------------------------------------------------
+ * DFMA / FFMA chain micro-benchmark: the compute-roofline denominator.  Returns
+ * achieved TFLOP/s (FMA = 2 flop) in *tflops; runs on the current device.        */
+int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms);
+/* counters of kernels launched by this library since load (all threads)          */
+int64_t acro_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACRO_B200_H */
