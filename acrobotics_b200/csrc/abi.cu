@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,6 +26,7 @@ struct AcroScene {
   int device;
   double* dev64;
   float* dev32;
+  CullTable cull;  // FP32 face-axis cull table (kernel parameter of the wavefront K2)
 };
 
 namespace {
@@ -147,6 +149,59 @@ int check_batch(const void* robot, const void* in, const void* out, int64_t n) {
 
 int finish(cudaError_t e, const char* where) { return e == cudaSuccess ? 0 : cuda_fail(e, where); }
 
+// ACRO_K2_VARIANT=simple selects the one-thread-per-configuration kernel of fk_cc.cu
+// for the plain FP64 path (A/B measurements, cross-checks); default: fk_cc_sm.cu
+// ACRO_K2_VARIANT selects the kernel behind the plain FP64 K2 path (A/B measurements,
+// cross-checks): "wave" (default, fk_cc_wave.cu), "sm" (fk_cc_sm.cu), "simple" (fk_cc.cu)
+int k2_variant() {
+  static const int variant = [] {
+    const char* v = std::getenv("ACRO_K2_VARIANT");
+    if (!v) return 0;
+    const std::string s(v);
+    return s == "simple" ? 2 : (s == "sm" ? 1 : 0);
+  }();
+  return variant;
+}
+
+float round_up_to_float(double x) {
+  float f = (float)x;
+  if ((double)f < x) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+// see CullTable in acro_device.cuh
+void build_cull_table(const double* packed, int n, CullTable& ct) {
+  std::memset(&ct, 0, sizeof(ct));
+  for (int j = 0; j < n; ++j) {
+    const double* b = packed + (size_t)j * kSceneStride;
+    double t[3];
+    for (int k = 0; k < 3; ++k)
+      t[k] = -(b[k] * b[9] + b[3 + k] * b[10] + b[6 + k] * b[11]);
+    const double tn = std::fabs(t[0]) + std::fabs(t[1]) + std::fabs(t[2]);
+    float* e = ct.e[j];
+    for (int k = 0; k < 3; ++k) {
+      e[4 * k + 0] = (float)b[k];
+      e[4 * k + 1] = (float)b[3 + k];
+      e[4 * k + 2] = (float)b[6 + k];
+      e[4 * k + 3] = (float)t[k];
+      e[12 + k] = round_up_to_float(b[12 + k] * (1.0 + 1e-6) + 1e-6 * tn);
+    }
+  }
+}
+
+cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
+                          int64_t n, int layout, uint32_t* mask, cudaStream_t st) {
+  const int variant = k2_variant();
+  if (variant == 2 || (variant == 0 && !wave_supports(robot->d64)))
+    return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, nullptr,
+                                0.0, st);
+  if (variant == 1)
+    return launch_fk_cc_sm(robot->d64, view_of<double>(scene), q, n, layout, mask, st);
+  static const CullTable empty_table = {};
+  return launch_fk_cc_wave(robot->d64, scene ? scene->cull : empty_table, view_of<double>(scene),
+                           q, n, layout, mask, st);
+}
+
 }  // namespace
 
 namespace acro {
@@ -226,7 +281,12 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
   }
   std::vector<float> p32(p64.size());
   for (size_t k = 0; k < p64.size(); ++k) p32[k] = (float)p64[k];
-  AcroScene* s = new AcroScene{n, 0, nullptr, nullptr};
+  AcroScene* s = new AcroScene;
+  s->n = n;
+  s->device = 0;
+  s->dev64 = nullptr;
+  s->dev32 = nullptr;
+  build_cull_table(p64.data(), n, s->cull);
   cudaError_t e = cudaGetDevice(&s->device);
   if (e == cudaSuccess) e = cudaMalloc(&s->dev64, p64.size() * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->dev32, p32.size() * sizeof(float));
@@ -287,6 +347,9 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
                    void* stream) {
   if (int rc = check_batch(robot, q, mask, n)) return rc;
   if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
+  if (!near_mask)
+    return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream)),
+                  "acro_fk_cc_f64");
   return finish(launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, q_layout, mask,
                                      near_mask, margin, as_stream(stream)),
                 "acro_fk_cc_f64");
@@ -365,8 +428,7 @@ int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const do
     e = cudaMemcpyAsync(g_pipe.d_q[slot], q_host + done * ndof, sizeof(double) * m * ndof,
                         cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
-      e = launch_fk_cc<double>(robot->d64, view_of<double>(scene), g_pipe.d_q[slot], m,
-                               ACRO_Q_AOS, g_pipe.d_mask[slot], nullptr, 0.0, st);
+      e = run_fk_cc_f64(robot, scene, g_pipe.d_q[slot], m, ACRO_Q_AOS, g_pipe.d_mask[slot], st);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(mask_host + done / 32, g_pipe.d_mask[slot],
                           sizeof(uint32_t) * ((m + 31) / 32), cudaMemcpyDeviceToHost, st);

@@ -66,6 +66,16 @@ struct SceneView {
   int32_t n;
 };
 
+// FP32 cull table of a scene (kernel parameter of the wavefront K2 kernel, read
+// with warp-uniform constant loads).  Entry j describes scene box j in its own frame:
+//  e[4k..4k+3], k = 0..2 : column k of R2 and t'_k = -(R2^T T2)_k, so that a point c has
+//                          box-frame coordinate y_k = col_k . c + t'_k
+//  e[12..14]             : B_k (1 + 1e-6) + 1e-6 |t'|_1, rounded up (padded half extents)
+//  e[15]                 : unused
+struct CullTable {
+  float e[kMaxScene][16];
+};
+
 // ---------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------
