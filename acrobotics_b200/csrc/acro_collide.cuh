@@ -30,33 +30,36 @@ __device__ __forceinline__ bool sat_separated(const real A0, const real A1, cons
 #pragma unroll
   for (int k = 0; k < 9; ++k) R2[k] = b2[kOB_R + k];
 
-  // pp = R1^T p ; R = R1^T R2 ; Q = |R|
-  real pp[3], R[9], Q[9];
+  // R = R1^T R2 ; Q = |R| ; pp = R1^T p.  The order in which the 15 axes are
+  // visited is free (the verdict is "no axis separates"); box 2's face axes go
+  // first and R is built column by column for them: they are the axes the
+  // bounding-sphere cull pre-tested, and for plate-like obstacles (a table) they
+  // are the ones that separate.
+  real R[9], Q[9];
+  const real A[3] = {A0, A1, A2};
+  const real B[3] = {B0, B1, B2};
+  real g = real(-1e30);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    pp[i] = fma_t(R1[6 + i], p2, fma_t(R1[3 + i], p1, R1[i] * p0));
+  for (int j = 0; j < 3; ++j) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int i = 0; i < 3; ++i) {
       R[3 * i + j] = fma_t(R1[6 + i], R2[6 + j], fma_t(R1[3 + i], R2[3 + j], R1[i] * R2[j]));
       Q[3 * i + j] = abs_t(R[3 * i + j]);
     }
-  }
-  const real A[3] = {A0, A1, A2};
-  const real B[3] = {B0, B1, B2};
-
-  // face axes of box 1 (u1,u2,u3)
-  real g = abs_t(pp[0]) - (fma_t(Q[2], B2, fma_t(Q[1], B1, Q[0] * B0)) + A0);
-  g = max(g, abs_t(pp[1]) - (fma_t(Q[5], B2, fma_t(Q[4], B1, Q[3] * B0)) + A1));
-  g = max(g, abs_t(pp[2]) - (fma_t(Q[8], B2, fma_t(Q[7], B1, Q[6] * B0)) + A2));
-  if (g > thr) return true;
-
-  // face axes of box 2 (v1,v2,v3)
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
+    // face axis v_j of box 2
     const real t = fma_t(R2[6 + j], p2, fma_t(R2[3 + j], p1, R2[j] * p0));
     const real rad = fma_t(Q[6 + j], A2, fma_t(Q[3 + j], A1, Q[j] * A0)) + B[j];
     g = max(g, abs_t(t) - rad);
   }
+  if (g > thr) return true;
+
+  // face axes of box 1 (u1,u2,u3)
+  real pp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pp[i] = fma_t(R1[6 + i], p2, fma_t(R1[3 + i], p1, R1[i] * p0));
+  g = max(g, abs_t(pp[0]) - (fma_t(Q[2], B2, fma_t(Q[1], B1, Q[0] * B0)) + A0));
+  g = max(g, abs_t(pp[1]) - (fma_t(Q[5], B2, fma_t(Q[4], B1, Q[3] * B0)) + A1));
+  g = max(g, abs_t(pp[2]) - (fma_t(Q[8], B2, fma_t(Q[7], B1, Q[6] * B0)) + A2));
   if (g > thr) return true;
 
   // nine edge x edge axes with ODE's fudge on |R|; FCL compares with eps here
