@@ -34,6 +34,20 @@ WORKLOAD = "Kuka 6-DOF fused FK+collision vs 16-box synthetic Scene (seed 0), q~
 # FK 63 flop/joint * 6 + 18 flop/link box * 6 = 486; 6*16 + 6 = 102 box pairs * 252 flop
 W_FULL_FLOP = 486 + 102 * 252
 BYTES_PER_CONFIG = 48.125  # 6 f64 in, 1 bit out
+K2_KERNEL = "acro::fk_cc_wave_kernel<512,128,4>"
+
+
+def _load_k2_profile():
+    """Per-configuration counters of the production K2 kernel from its last ncu
+    --set full capture (written by tools/ncu_k2_profile.py, tracked under profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k2_profile.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+K2_PROFILE = _load_k2_profile()
 
 
 # ----------------------------------------------------------------------------
@@ -320,15 +334,29 @@ def run_ours(args):
                 "collision_rate": round(collision_rate, 4),
             },
             "roofline": {
-                "bound": "fp64", "kernel": "fk_cc_kernel<double,6,false>",
+                "bound": "fp64", "kernel": K2_KERNEL,
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak, "traffic": None,
-                "note": ("achieved = algorithmic W_full (26190 flop/config, no culling, SURVEY 8d) "
-                         "* configs / kernel time; peak = DFMA-chain measured in this run "
-                         "(MEASURED_PEAKS.json has no FP64 figure); culling and early exit make "
-                         "the executed flop count smaller than W_full, see DESIGN.md"),
+                "frac": achieved / fp64_peak,
+                "traffic": K2_PROFILE.get("dram_bytes_per_config", 0) * n or None,
+                "note": ("compute-bound CUDA-core kernel (no GEMM shape): achieved = algorithmic "
+                         "W_full (26190 flop/config, no culling, SURVEY 8d) * configs / kernel "
+                         "time, so culling and early exits push it above 1; peak = DFMA chain "
+                         "measured in this run (MEASURED_PEAKS.json has no FP64 figure). "
+                         "'executed' = flop the kernel really issues (ncu counters, "
+                         "profiles/k2_profile.json) over the same time; 'hbm' = the input/output "
+                         "stream against the measured copy bandwidth. traffic = ncu dram bytes "
+                         "per configuration * configs"),
                 "kernel_ms": kms,
-                "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "executed": {
+                    "fp64_flop_per_config": K2_PROFILE.get("fp64_flop_per_config"),
+                    "fp32_flop_per_config": K2_PROFILE.get("fp32_flop_per_config"),
+                    "thread_inst_per_config": K2_PROFILE.get("thread_inst_per_config"),
+                    "fp64_tflops": (K2_PROFILE.get("fp64_flop_per_config", 0) * n / (kms * 1e-3) / 1e12),
+                    "frac_of_fp64_peak": (K2_PROFILE.get("fp64_flop_per_config", 0) * n
+                                          / (kms * 1e-3) / 1e12 / fp64_peak),
+                    "source": K2_PROFILE.get("source"),
+                },
+                "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_gbs / hbm_peak,
                         "peak_source": "measured" if peaks else "fallback"},
             },
