@@ -67,10 +67,12 @@ SIGNATURES = {
     "acro_last_error": (C.c_char_p, []),
     "acro_device_count": (C.c_int, []),
     "acro_launch_count": (_I64, []),
+    "acro_set_option": (C.c_int, [C.c_char_p, C.c_char_p]),
     "acro_robot_create": (C.c_int, [C.POINTER(AcroRobotDesc), C.POINTER(_P)]),
     "acro_robot_destroy": (None, [_P]),
     "acro_scene_create": (C.c_int, [C.POINTER(AcroBox), _I32, C.POINTER(_P)]),
     "acro_scene_destroy": (None, [_P]),
+    "acro_scene_prepare": (C.c_int, [_P, _P]),
     "acro_collide_boxes_f64": (C.c_int, [_P, _P, _I64, _P, _P]),
     "acro_fk_f64": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
     "acro_fk_f32": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
@@ -122,3 +124,8 @@ def check(rc, what=""):
 
 def launch_count():
     return int(load().acro_launch_count())
+
+
+def set_option(name, value):
+    """Process-wide tuning knob (see ``acro_set_option`` in include/acro_b200.h)."""
+    check(load().acro_set_option(str(name).encode(), str(value).encode()), "acro_set_option")

@@ -19,6 +19,23 @@ struct AcroRobot {
   AcroRobotDesc desc;
   RobotDev<double> d64;
   RobotDev<float> d32;
+  // filtered K2: distinct bounding radii of the boxes, and the cube the boxes can reach
+  int n_classes;
+  double class_radius[ACRO_MAX_ROBOT_BOXES];
+  double centre[3];   // base position
+  double reach;       // bound on |box centre - base position| + box radius
+  double q_lin_max;   // prismatic travel covered by `reach`
+};
+
+// Candidate grid + filter tolerance of one (robot geometry, scene) pair; see GridView.
+struct CullPlan {
+  int n_classes;
+  double class_radius[ACRO_MAX_ROBOT_BOXES];
+  double centre[3], reach;
+  int dim;
+  int mask_bits;
+  void* cells;
+  GridView view;
 };
 
 struct AcroScene {
@@ -27,6 +44,10 @@ struct AcroScene {
   double* dev64;
   float* dev32;
   CullTable cull;  // FP32 face-axis cull table (kernel parameter of the wavefront K2)
+  double bound;    // max over boxes of |centre| + bounding radius
+  // plans are created on first use (or by acro_scene_prepare), never freed before the scene
+  mutable std::mutex mu;
+  mutable std::vector<CullPlan*> plans;
 };
 
 namespace {
@@ -105,6 +126,25 @@ int build_dev(const AcroRobotDesc& d, RobotDev<real>& o) {
     for (int e = 0; e < 12; ++e) bx.off[e] = (real)src.tf[e];
     bx.rot_identity = is_identity_rot(src.tf);
     bx.save_slot = -1;
+    bx.cull_class = 0;
+    bx.reserved = 0;
+  }
+  // radius classes (one candidate grid per distinct bounding radius)
+  {
+    std::vector<double> radii;
+    for (int k = 0; k < (int)order.size(); ++k) {
+      const AcroRobotBox& src = d.boxes[order[k]];
+      const double rad = std::sqrt(src.half[0] * src.half[0] + src.half[1] * src.half[1] +
+                                   src.half[2] * src.half[2]);
+      int cls = -1;
+      for (int c = 0; c < (int)radii.size(); ++c)
+        if (radii[c] == rad) cls = c;
+      if (cls < 0) {
+        cls = (int)radii.size();
+        radii.push_back(rad);
+      }
+      o.boxes[k].cull_class = cls;
+    }
   }
   // self pairs grouped by their later box (in processing order)
   std::vector<std::vector<int>> partners(d.n_boxes);
@@ -149,18 +189,112 @@ int check_batch(const void* robot, const void* in, const void* out, int64_t n) {
 
 int finish(cudaError_t e, const char* where) { return e == cudaSuccess ? 0 : cuda_fail(e, where); }
 
-// ACRO_K2_VARIANT=simple selects the one-thread-per-configuration kernel of fk_cc.cu
-// for the plain FP64 path (A/B measurements, cross-checks); default: fk_cc_sm.cu
+float round_up_to_float(double x);
+
 // ACRO_K2_VARIANT selects the kernel behind the plain FP64 K2 path (A/B measurements,
-// cross-checks): "wave" (default, fk_cc_wave.cu), "sm" (fk_cc_sm.cu), "simple" (fk_cc.cu)
+// cross-checks): "filter" (default, fk_cc_filt.cu), "wave" (fk_cc_wave.cu), "sm"
+// (fk_cc_sm.cu), "simple" (fk_cc.cu)
+std::atomic<int> g_k2_variant{-1};
+std::atomic<int> g_grid_dim{-1};
+
+int parse_variant(const std::string& s) {
+  if (s == "simple") return 2;
+  if (s == "sm") return 1;
+  if (s == "wave") return 0;
+  if (s == "filter") return 3;
+  return -1;
+}
+
 int k2_variant() {
-  static const int variant = [] {
-    const char* v = std::getenv("ACRO_K2_VARIANT");
-    if (!v) return 0;
-    const std::string s(v);
-    return s == "simple" ? 2 : (s == "sm" ? 1 : 0);
-  }();
-  return variant;
+  int v = g_k2_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("ACRO_K2_VARIANT");
+    v = e ? parse_variant(e) : 3;
+    if (v < 0) v = 3;
+    g_k2_variant.store(v);
+  }
+  return v;
+}
+
+int grid_dim_setting() {
+  int d = g_grid_dim.load(std::memory_order_relaxed);
+  if (d < 0) {
+    const char* e = std::getenv("ACRO_K2_GRID");
+    d = e ? std::atoi(e) : 64;
+    d = d < 8 ? 8 : (d > 160 ? 160 : d);
+    g_grid_dim.store(d);
+  }
+  return d;
+}
+
+// Find or build the candidate grid + filter tolerance for (robot geometry, scene).
+cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullPlan** out) {
+  std::lock_guard<std::mutex> lock(scene->mu);
+  for (const CullPlan* p : scene->plans) {
+    if (p->n_classes != robot->n_classes || p->reach != robot->reach ||
+        p->dim != grid_dim_setting())
+      continue;
+    bool same = p->centre[0] == robot->centre[0] && p->centre[1] == robot->centre[1] &&
+                p->centre[2] == robot->centre[2];
+    for (int c = 0; same && c < p->n_classes; ++c)
+      same = p->class_radius[c] == robot->class_radius[c];
+    if (same) {
+      *out = p;
+      return cudaSuccess;
+    }
+  }
+  CullPlan* p = new CullPlan();
+  p->n_classes = robot->n_classes;
+  for (int c = 0; c < p->n_classes; ++c) p->class_radius[c] = robot->class_radius[c];
+  for (int k = 0; k < 3; ++k) p->centre[k] = robot->centre[k];
+  p->reach = robot->reach;
+  p->dim = grid_dim_setting();
+  p->mask_bits = scene->n <= 32 ? 32 : 64;
+  p->cells = nullptr;
+  // FP32 filter tolerance: every SAT quantity is a sum of O(50) products of numbers
+  // bounded by the workspace size P; with unit roundoff 6e-8, sin/cos good to 1.2e-7 and six
+  // chained links the FP32 value stays within ~1e-5 P of the FP64 one.  Ten
+  // times that is used.
+  const double base_norm = std::sqrt(p->centre[0] * p->centre[0] + p->centre[1] * p->centre[1] +
+                                     p->centre[2] * p->centre[2]);
+  const double P = base_norm + robot->reach + scene->bound;
+  const double delta = 1.0e-4 * std::max(1.0, P);
+  const double half = std::max(robot->reach, 1e-3);
+  const double cell = 2.0 * half / p->dim;
+  const double origin[3] = {p->centre[0] - half, p->centre[1] - half, p->centre[2] - half};
+  p->view.cells = nullptr;
+  p->view.ox = (float)origin[0];
+  p->view.oy = (float)origin[1];
+  p->view.oz = (float)origin[2];
+  p->view.inv_cell = (float)(1.0 / cell);
+  p->view.dim = p->dim;
+  p->view.delta = round_up_to_float(delta);
+  p->view.q_lin_max = (float)robot->q_lin_max;
+  cudaError_t e = cudaSuccess;
+  if (scene->n > 0 && p->n_classes > 0) {
+    const size_t cells = (size_t)p->dim * p->dim * p->dim * p->n_classes;
+    double* d_rad = nullptr;
+    e = cudaMalloc(&p->cells, cells * (p->mask_bits / 8));
+    if (e == cudaSuccess) e = cudaMalloc(&d_rad, sizeof(double) * p->n_classes);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(d_rad, p->class_radius, sizeof(double) * p->n_classes, cudaMemcpyHostToDevice);
+    // pad: half diagonal of a cell + FP32 position error + index rounding slack
+    const double pad = 0.5 * cell * std::sqrt(3.0) * (1.0 + 1e-6) + delta + 1e-3 * cell;
+    if (e == cudaSuccess)
+      e = launch_build_grid(SceneView<double>{scene->dev64, scene->n}, p->cells, p->mask_bits,
+                            p->dim, p->n_classes, origin, cell, d_rad, pad, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_rad);
+    if (e != cudaSuccess) {
+      cudaFree(p->cells);
+      delete p;
+      return e;
+    }
+    p->view.cells = p->cells;
+  }
+  scene->plans.push_back(p);
+  *out = p;
+  return cudaSuccess;
 }
 
 float round_up_to_float(double x) {
@@ -189,10 +323,38 @@ void build_cull_table(const double* packed, int n, CullTable& ct) {
   }
 }
 
+constexpr int64_t kFilterMinBatch = 4096;  // below this the plain FP64 kernel is used
+
 cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
                           int64_t n, int layout, uint32_t* mask, cudaStream_t st) {
   const int variant = k2_variant();
-  if (variant == 2 || (variant == 0 && !wave_supports(robot->d64)))
+  if (variant == 3 && n >= kFilterMinBatch) {
+    static const AcroScene empty_scene{};
+    const AcroScene* sc = scene ? scene : &empty_scene;
+    const CullPlan* plan = nullptr;
+    cudaError_t e = get_plan(robot, sc, &plan);
+    if (e != cudaSuccess) return e;
+    // stream-ordered scratch for the ambiguity mask (one bit per configuration)
+    static std::once_flag pool_once;
+    std::call_once(pool_once, [] {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess &&
+          cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    });
+    uint32_t* amb = nullptr;
+    e = cudaMallocAsync(&amb, sizeof(uint32_t) * ((n + 31) / 32), st);
+    if (e != cudaSuccess) return e;
+    e = launch_fk_cc_filter(robot->d32, robot->d64, plan->view, plan->mask_bits,
+                            view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
+                            amb, st);
+    cudaError_t e2 = cudaFreeAsync(amb, st);
+    return e != cudaSuccess ? e : e2;
+  }
+  if (variant == 2 || variant == 3 || (variant == 0 && !wave_supports(robot->d64)))
     return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, nullptr,
                                 0.0, st);
   if (variant == 1)
@@ -227,6 +389,24 @@ int acro_device_count(void) {
   return n;
 }
 
+int acro_set_option(const char* name, const char* value) {
+  if (!name || !value) return fail(ACRO_E_INVALID, "NULL option");
+  const std::string n(name), v(value);
+  if (n == "k2_variant") {
+    const int k = parse_variant(v);
+    if (k < 0) return fail(ACRO_E_INVALID, "k2_variant: filter | wave | sm | simple");
+    g_k2_variant.store(k);
+    return 0;
+  }
+  if (n == "k2_grid") {
+    const int d = std::atoi(value);
+    if (d < 8 || d > 160) return fail(ACRO_E_INVALID, "k2_grid: 8..160 cells per axis");
+    g_grid_dim.store(d);
+    return 0;
+  }
+  return fail(ACRO_E_INVALID, "unknown option");
+}
+
 int acro_robot_create(const AcroRobotDesc* desc, AcroRobot** out) {
   if (!desc || !out) return fail(ACRO_E_INVALID, "NULL argument");
   *out = nullptr;
@@ -255,6 +435,24 @@ int acro_robot_create(const AcroRobotDesc* desc, AcroRobot** out) {
     delete r;
     return fail(ACRO_E_UNSUPPORTED, "too many boxes take part in self-collision pairs");
   }
+  // geometry summary for the filtered K2 kernel
+  r->n_classes = 0;
+  double box_reach = 0.0;
+  for (int b = 0; b < r->d64.n_boxes; ++b) {
+    const BoxDev<double>& bx = r->d64.boxes[b];
+    if (bx.cull_class + 1 > r->n_classes) r->n_classes = bx.cull_class + 1;
+    r->class_radius[bx.cull_class] = bx.radius;  // already rounded up
+    const double off = std::sqrt(bx.off[3] * bx.off[3] + bx.off[7] * bx.off[7] + bx.off[11] * bx.off[11]);
+    box_reach = std::max(box_reach, off + bx.radius);
+  }
+  r->q_lin_max = 4.0;
+  double chain = 0.0;
+  for (int i = 0; i < desc->ndof; ++i)
+    chain += std::fabs(desc->a[i]) + (desc->joint_type[i] ? r->q_lin_max : std::fabs(desc->d[i]));
+  r->reach = chain + box_reach;
+  r->centre[0] = desc->tf_base[3];
+  r->centre[1] = desc->tf_base[7];
+  r->centre[2] = desc->tf_base[11];
   *out = r;
   return 0;
 }
@@ -266,6 +464,7 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
   *out = nullptr;
   if (n > ACRO_MAX_SCENE_BOXES) return fail(ACRO_E_UNSUPPORTED, "too many scene boxes");
   std::vector<double> p64((size_t)(n > 0 ? n : 1) * kSceneStride, 0.0);
+  double bound = 0.0;
   for (int j = 0; j < n; ++j) {
     double* o = &p64[(size_t)j * kSceneStride];
     double r2 = 0, hmax = 0;
@@ -278,11 +477,13 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
     }
     o[15] = std::sqrt(r2) * (1.0 + 1e-6);
     o[16] = hmax;
+    bound = std::max(bound, std::sqrt(o[9] * o[9] + o[10] * o[10] + o[11] * o[11]) + o[15]);
   }
   std::vector<float> p32(p64.size());
   for (size_t k = 0; k < p64.size(); ++k) p32[k] = (float)p64[k];
   AcroScene* s = new AcroScene;
   s->n = n;
+  s->bound = bound;
   s->device = 0;
   s->dev64 = nullptr;
   s->dev32 = nullptr;
@@ -307,9 +508,19 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
 
 void acro_scene_destroy(AcroScene* scene) {
   if (!scene) return;
+  for (CullPlan* p : scene->plans) {
+    cudaFree(p->cells);
+    delete p;
+  }
   cudaFree(scene->dev64);
   cudaFree(scene->dev32);
   delete scene;
+}
+
+int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot) {
+  if (!scene || !robot) return fail(ACRO_E_INVALID, "NULL handle");
+  const CullPlan* plan = nullptr;
+  return finish(get_plan(robot, scene, &plan), "acro_scene_prepare");
 }
 
 int acro_collide_boxes_f64(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,

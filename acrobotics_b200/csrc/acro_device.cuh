@@ -34,6 +34,8 @@ struct BoxDev {
   real off[12];  // 3x4 offset in the carrier frame
   int32_t save_slot;     // >= 0: world pose is kept for later self pairs
   int32_t rot_identity;  // offset is a pure translation
+  int32_t cull_class;    // index of this box's bounding radius among the robot's distinct radii
+  int32_t reserved;
 };
 
 template <typename real>
@@ -74,6 +76,21 @@ struct SceneView {
 //  e[15]                 : unused
 struct CullTable {
   float e[kMaxScene][16];
+};
+
+// Candidate grid of a (robot, scene) pair (kernel parameter of the filtered K2 kernel).
+// A cube of dim^3 cells around the robot base; cells[(cls * dim^3) + (iz*dim + iy)*dim + ix]
+// is a bit set over the scene boxes: bit j is CLEAR only if, for every point c of the
+// (slightly enlarged) cell, a sphere of the class radius around c is separated from scene
+// box j along one of that box's face axes - i.e. FCL's own face-axis test separates every
+// robot box of that radius class centred anywhere in the cell.
+struct GridView {
+  const void* cells;  // uint32 words when the scene has <= 32 boxes, else uint64
+  float ox, oy, oz;   // lower corner
+  float inv_cell;
+  int32_t dim;
+  float delta;        // FP32 filter tolerance (bound on |s_fp32 - s_fp64| of any SAT quantity)
+  float q_lin_max;    // prismatic joint travel covered by the bound
 };
 
 // ---------------------------------------------------------------------------

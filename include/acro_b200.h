@@ -100,6 +100,13 @@ const char* acro_last_error(void);
 /* number of CUDA devices visible, <0 on error; never initialises a context */
 int acro_device_count(void);
 
+/* Tuning knobs (process wide; defaults are the production settings):
+ *   "k2_variant" = "filter" (default) | "wave" | "sm" | "simple": kernel behind acro_fk_cc_f64
+ *                  without a near mask; all variants return identical verdicts;
+ *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 64).
+ * The environment variables ACRO_K2_VARIANT / ACRO_K2_GRID set the initial values.    */
+int acro_set_option(const char* name, const char* value);
+
 /* Robot(links, joint_limits) + geometry  ->  immutable device descriptor.
  * Replaces the per-call Python object walk in robot.py:244-273.                  */
 int acro_robot_create(const AcroRobotDesc* desc, AcroRobot** out);
@@ -108,6 +115,12 @@ void acro_robot_destroy(AcroRobot* robot);
 /* Scene(shapes, tf_shapes) (geometry.py:12-14), boxes only.  n may be 0.         */
 int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out);
 void acro_scene_destroy(AcroScene* scene);
+/* Optional: build now what acro_fk_cc_f64 would otherwise build on its first call with
+ * this (robot, scene) pair - the candidate grid of the filtered kernel (a few MB of
+ * device memory owned by the scene handle, one synchronisation).  After it, the hot call
+ * allocates nothing but stream-ordered scratch (cudaMallocAsync) for one bit per
+ * configuration.                                                                   */
+int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot);
 
 /* ---- the fcl.collide seam -------------------------------------------------------
  * n independent Box-Box tests: a[i] against b[i] (each an AcroBox with its WORLD

@@ -1,0 +1,117 @@
+"""K2 kernel variants: the filtered production kernel (FP32 filter + candidate grid +
+exact FP64 fix-up) must return exactly the verdicts of the plain FP64 kernel - on random
+batches, on inputs built to sit on the filter's ambiguity band (aligned boxes, grazing
+contact), outside the candidate grid, and for joint values the FP32 chain cannot follow."""
+import numpy as np
+import pytest
+from conftest import golden
+from helpers import kuka_with_tool, spec
+
+import acrobotics_b200 as ab
+from acrobotics_b200 import _native
+from acrobotics_b200.synthetic import random_configs, readme_scene, scene16
+from acrobotics_b200.transforms import translation
+from oracle import np_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_variant(name, fn):
+    _native.set_option("k2_variant", name)
+    try:
+        return fn()
+    finally:
+        _native.set_option("k2_variant", "filter")
+
+
+def _all_variants_agree(robot, q, scene, self_only=False):
+    call = (lambda: robot.is_in_self_collision_batch(q)) if self_only else (
+        lambda: robot.is_in_collision_batch(q, scene))
+    ref = _with_variant("simple", call)
+    got = _with_variant("filter", call)
+    assert (got == ref).all(), f"{int((got != ref).sum())} of {len(q)} verdicts differ"
+    return ref
+
+
+def test_filter_equals_fp64_on_random_batches(gpu):
+    g = golden("cc_kuka.npz")
+    q = random_configs(2_000_000, 6, seed=11)
+    k = ab.Kuka()
+    for scene in (scene16(), readme_scene(), scene16(seed=5, n_boxes=40), ab.Scene([], [])):
+        hit = _all_variants_agree(k, q, scene)
+        assert 0.05 < hit.mean() < 0.99
+    _all_variants_agree(k, q, None, self_only=True)
+    wave = _with_variant("wave", lambda: k.is_in_collision_batch(q, scene16()))
+    assert (wave == k.is_in_collision_batch(q, scene16())).all()
+    # tool + base geometry + moved base, prismatic first joint
+    _all_variants_agree(kuka_with_tool(g), q[:500_000], scene16())
+    _all_variants_agree(ab.KukaOnRail(), random_configs(500_000, 7, seed=16), scene16())
+    k.do_check_self_collision = False
+    _all_variants_agree(k, q[:500_000], scene16())
+
+
+def test_filter_vs_oracle(gpu):
+    k = ab.Kuka()
+    scene = scene16()
+    q = random_configs(300_000, 6, seed=12)
+    hit = k.is_in_collision_batch(q, scene)
+    gq = no.collision_margins(spec(k), scene, q)
+    robust = np.abs(gq) > 1e-6
+    assert (hit[robust] == ~(gq[robust] > 0)).all()
+    assert (~robust).mean() < 1e-3
+
+
+def test_filter_ambiguity_band(gpu):
+    """Configurations engineered to land inside the filter tolerance: axis-aligned boxes
+    (degenerate edge axes), links grazing an obstacle face within 1e-7 .. 1e-4 m."""
+    k = ab.Kuka()
+    rng = np.random.default_rng(3)
+    n = 8192
+    # joint angles on multiples of pi/2 keep every link box axis-aligned with the scene
+    q_aligned = rng.integers(-2, 3, (n, 6)) * (np.pi / 2)
+    q_aligned[::2] += rng.normal(0, 1e-7, (n // 2, 6))
+    _all_variants_agree(k, q_aligned, readme_scene())
+    # a wall whose face sits within +-gap of link 2's box face for q = 0 pose:
+    # sweep the wall position through contact
+    T = k.fk_batch(np.zeros((1, 6)), all_links=True)[0]
+    c = T[1] @ np.array([-0.3, 0, -0.05, 1.0])  # centre of link-1 box
+    for gap in (1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 0.0, -1e-7, -1e-5):
+        wall = ab.Scene([ab.Box(0.2, 2.0, 2.0)],
+                        [translation(c[0] + 0.4 + 0.1 + gap, c[1], c[2])])
+        qs = np.zeros((n, 6))
+        qs[:, 3:] = rng.uniform(-3, 3, (n, 3))  # wrist moves, link 1 does not
+        qs[:, 0] = rng.normal(0, 1e-6, n)
+        _all_variants_agree(k, qs, wall)
+
+
+def test_filter_out_of_range_inputs(gpu):
+    k = ab.Kuka()
+    scene = scene16()
+    n = 8192
+    q = random_configs(n, 6, seed=13)
+    q[::7] *= 1e3          # large angles: FP64 argument reduction still exact
+    q[5::11] *= 1e9        # beyond the filter's range: decided by the FP64 pass
+    q[3::13, 2] = np.nan   # NaN joints: whatever the FP64 kernel says
+    q[1::17, 4] = np.inf
+    _all_variants_agree(k, q, scene)
+    # rail far outside the candidate grid (prismatic travel beyond the covered range)
+    rail = ab.KukaOnRail()
+    qr = random_configs(n, 7, seed=14)
+    qr[:, 0] *= 3.0
+    _all_variants_agree(rail, qr, scene)
+    # a scene that is far away / huge compared with the robot
+    far = ab.Scene([ab.Box(50, 50, 1.0), ab.Box(1, 1, 1)],
+                   [translation(0, 0, -0.55), translation(30, 0, 0)])
+    _all_variants_agree(k, q, far)
+
+
+def test_grid_resolution_does_not_change_verdicts(gpu):
+    k = ab.Kuka()
+    q = random_configs(200_000, 6, seed=15)
+    ref = _with_variant("simple", lambda: k.is_in_collision_batch(q, scene16()))
+    try:
+        for dim in (8, 32, 100):
+            _native.set_option("k2_grid", dim)
+            assert (k.is_in_collision_batch(q, scene16()) == ref).all()
+    finally:
+        _native.set_option("k2_grid", 64)

@@ -6,9 +6,15 @@ import sys
 
 path, block = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = list(csv.reader(open(path)))
-hdr = rows[1]
+# the CSV holds one segment per profiled launch: "Kernel Name" row, header row, instructions
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+lo_seg = starts[which]
+hi_seg = starts[which + 1] if which + 1 < len(starts) else len(rows)
+print(rows[lo_seg][1][:100])
+hdr = rows[lo_seg + 1]
 col = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = rows[lo_seg + 2:hi_seg]
 tot_s = sum(float(r[col["# Samples"]] or 0) for r in data)
 tot_i = sum(float(r[col["Instructions Executed"]] or 0) for r in data)
 print(f"total samples {tot_s:.0f}, warp instructions {tot_i:.3e}")
