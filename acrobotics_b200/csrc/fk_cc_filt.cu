@@ -310,10 +310,56 @@ __global__ void __launch_bounds__(kFThreads, 4)
           }
         }
 
-        // ---- rounds: the warp's candidate pairs, redistributed over its lanes
+        // ---- rounds over the warp's candidate pairs.  A round is "direct" (every lane
+        // tests its own next candidate with its own pose: no data movement) when most lanes
+        // have one, or no lane has more than one; otherwise the remaining pairs of the whole
+        // warp are redistributed over its lanes (items in a shared-memory list, the owner's
+        // pose fetched with shuffles) so that the 15-axis test still runs on dense warps.
+        auto load_other = [&](int other, int owner, float* R2, float* T2, float& B0, float& B1,
+                              float& B2) {
+          if (other < 64) {
+            const float* ob = s_scene + other * kSceneStrideF;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R2[e] = ob[e];
+            T2[0] = ob[9]; T2[1] = ob[10]; T2[2] = ob[11];
+            B0 = ob[12]; B1 = ob[13]; B2 = ob[14];
+          } else {
+            const int sl = other - 64;
+            const float* sv = s_saved + sl * 12 * 32 + owner;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R2[e] = sv[e * 32];
+            T2[0] = sv[9 * 32]; T2[1] = sv[10 * 32]; T2[2] = sv[11 * 32];
+            B0 = s_half[4 * sl]; B1 = s_half[4 * sl + 1]; B2 = s_half[4 * sl + 2];
+          }
+        };
         for (;;) {
           const int c = done ? 0 : popc_t<MaskT>(ms) + __popc(mself);
-          if (!__any_sync(kFull, c > 0)) break;
+          const unsigned b1 = __ballot_sync(kFull, c > 0);
+          if (b1 == 0u) break;
+          const unsigned b2 = __ballot_sync(kFull, c > 1);
+          if (b2 == 0u || __popc(b1) >= 20) {
+            if (c > 0) {
+              int other;
+              if (ms != 0) {
+                other = ffs_t<MaskT>(ms);
+                ms &= ms - 1;
+              } else {
+                other = 64 + __ffs((int)mself) - 1;
+                mself &= mself - 1;
+              }
+              float R2[9], T2[3], B0, B1, B2;
+              load_other(other, (int)lane, R2, T2, B0, B1, B2);
+              const int res = sat_filter(A0, A1, A2, Rw, cw, R2, T2, B0, B1, B2, delta);
+              if (res == kHit) {
+                hit = true;
+                done = true;
+              } else if (res == kAmb) {
+                amb = true;
+              }
+            }
+            __syncwarp();
+            continue;
+          }
           int incl = c;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -350,20 +396,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
             int res = kSep;
             if (valid && !owner_done) {
               float R2[9], T2[3], B0, B1, B2;
-              if (other < 64) {
-                const float* ob = s_scene + other * kSceneStrideF;
-#pragma unroll
-                for (int e = 0; e < 9; ++e) R2[e] = ob[e];
-                T2[0] = ob[9]; T2[1] = ob[10]; T2[2] = ob[11];
-                B0 = ob[12]; B1 = ob[13]; B2 = ob[14];
-              } else {
-                const int sl = other - 64;
-                const float* sv = s_saved + sl * 12 * 32 + owner;
-#pragma unroll
-                for (int e = 0; e < 9; ++e) R2[e] = sv[e * 32];
-                T2[0] = sv[9 * 32]; T2[1] = sv[10 * 32]; T2[2] = sv[11 * 32];
-                B0 = s_half[4 * sl]; B1 = s_half[4 * sl + 1]; B2 = s_half[4 * sl + 2];
-              }
+              load_other(other, owner, R2, T2, B0, B1, B2);
               res = sat_filter(A0, A1, A2, R1, c1, R2, T2, B0, B1, B2, delta);
             }
             const unsigned hb = __reduce_or_sync(kFull, res == kHit ? (1u << owner) : 0u);
