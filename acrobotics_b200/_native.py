@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacro_b200.so")
+# ACRO_B200_LIB selects an alternative build of the same library (tuning variants)
+LIB_PATH = os.environ.get("ACRO_B200_LIB") or os.path.join(_HERE, "libacro_b200.so")
 
 MAX_DOF = 8
 MAX_ROBOT_BOXES = 24

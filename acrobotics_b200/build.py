@@ -63,6 +63,29 @@ def _compile(src, verbose):
     return obj, p.stderr
 
 
+def build_variant(tag, defines):
+    """Tuning aid: build libacro_b200_<tag>.so with extra -D defines (selected at run
+    time with ACRO_B200_LIB=<path>); objects go to _obj/<tag>/."""
+    global OBJ_DIR
+    saved_obj, saved_flags = OBJ_DIR, list(NVCC_FLAGS)
+    OBJ_DIR = os.path.join(saved_obj, tag)
+    NVCC_FLAGS.extend(f"-D{d}" for d in defines)
+    try:
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        with cf.ThreadPoolExecutor(max_workers=8) as ex:
+            objs = [o for o, _ in ex.map(lambda s: _compile(s, False), SOURCES)]
+        out = os.path.join(HERE, f"libacro_b200_{tag}.so")
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs,
+               "-lcudart"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+        return out
+    finally:
+        OBJ_DIR = saved_obj
+        NVCC_FLAGS[:] = saved_flags
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA translation unit for sm_100a and link the C-ABI library."""
     if not force and not is_stale():
@@ -91,5 +114,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

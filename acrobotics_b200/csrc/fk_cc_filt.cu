@@ -36,6 +36,12 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kFThreads = 128;
 constexpr int kItemCap = 64;      // candidate pairs per warp and round
+#ifndef ACRO_FILTER_MIN_CTAS
+#define ACRO_FILTER_MIN_CTAS 5
+#endif
+#ifndef ACRO_FILTER_DIRECT_MIN
+#define ACRO_FILTER_DIRECT_MIN 20
+#endif
 constexpr int kSceneStrideF = 16; // floats per scene box: R2 row-major, T2, B, radius
 
 enum : int { kSep = 0, kHit = 1, kAmb = 2 };
@@ -152,7 +158,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 template <int NDOF, typename MaskT>
-__global__ void __launch_bounds__(kFThreads, 4)
+__global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved,
                         const double* __restrict__ q, const int64_t n, const int layout,
@@ -284,8 +290,8 @@ __global__ void __launch_bounds__(kFThreads, 4)
             const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
             const unsigned dim = (unsigned)grid.dim;
             if ((unsigned)ix < dim && (unsigned)iy < dim && (unsigned)iz < dim) {
-              const size_t cell =
-                  ((size_t)bx.cull_class * dim + iz) * dim * dim + (size_t)iy * dim + ix;
+              // < 2^32 cells by construction (24 classes x 160^3)
+              const unsigned cell = (((unsigned)bx.cull_class * dim + iz) * dim + iy) * dim + ix;
               ms = __ldg(reinterpret_cast<const MaskT*>(grid.cells) + cell);
             } else {
               ms = n_scene >= (int)(8 * sizeof(MaskT)) ? ~MaskT(0) : ((MaskT(1) << n_scene) - 1);
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
           const unsigned b1 = __ballot_sync(kFull, c > 0);
           if (b1 == 0u) break;
           const unsigned b2 = __ballot_sync(kFull, c > 1);
-          if (b2 == 0u || __popc(b1) >= 20) {
+          if (b2 == 0u || __popc(b1) >= ACRO_FILTER_DIRECT_MIN) {
             if (c > 0) {
               int other;
               if (ms != 0) {

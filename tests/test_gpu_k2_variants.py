@@ -114,4 +114,4 @@ def test_grid_resolution_does_not_change_verdicts(gpu):
             _native.set_option("k2_grid", dim)
             assert (k.is_in_collision_batch(q, scene16()) == ref).all()
     finally:
-        _native.set_option("k2_grid", 64)
+        _native.set_option("k2_grid", 96)

@@ -44,7 +44,8 @@ ops = {op: per_config(op) for op in ("dfma", "dmul", "dadd", "ffma", "fmul", "fa
 prof = {
     "kernel": d["Kernel Name"].split("(")[0].replace("void ", ""),
     "configs_per_launch": n,
-    "gpu_time_ms": f("gpu__time_duration.sum"),
+    "gpu_time_ms": f("gpu__time_duration.sum") * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(
+        rows[1][hdr.index("gpu__time_duration.sum")], 1.0),
     "thread_inst_per_config": f("sass__thread_inst_executed_true_per_opcode") / n
     if "sass__thread_inst_executed_true_per_opcode" in d else None,
     "warp_inst_per_config": f("smsp__inst_executed.sum") / n,
