@@ -1,6 +1,8 @@
 // acro_launch.h - internal C++ launch interface between the kernel translation
 // units and the C ABI (abi.cu).  Not part of the public interface.
 #pragma once
+#include <cstdint>
+
 #include "acro_device.cuh"
 
 namespace acro {
@@ -90,6 +92,118 @@ __device__ __forceinline__ void load_q(real* qv, real* s_q, const real* __restri
   } else {
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) qv[i] = idx < n ? q[(int64_t)i * n + idx] : real(0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// direct per-thread row I/O for the streaming (HBM-bound) kernels: every thread moves
+// its own row of W reals with 16-byte accesses when the row is 16-byte aligned (even W
+// for doubles, W % 4 == 0 for floats, 16-byte aligned base), else element by element.  A warp's
+// accesses cover one contiguous span, so every 32-byte sector fetched is fully used.
+// ---------------------------------------------------------------------------
+template <typename real, int W>
+__device__ __forceinline__ void load_row(real* dst, const real* __restrict__ src, bool vec) {
+  constexpr int PER = 16 / sizeof(real);
+  if (W % PER == 0 && vec) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+#pragma unroll
+    for (int k = 0; k < W / PER; ++k) {
+      const int4 v = __ldg(s4 + k);
+      reinterpret_cast<int4*>(dst)[k] = v;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < W; ++k) dst[k] = __ldg(src + k);
+  }
+}
+
+template <typename real, int W>
+__device__ __forceinline__ void store_row(real* __restrict__ dst, const real* src, bool vec) {
+  constexpr int PER = 16 / sizeof(real);
+  if (W % PER == 0 && vec) {
+    int4* d4 = reinterpret_cast<int4*>(dst);
+#pragma unroll
+    for (int k = 0; k < W / PER; ++k) __stcs(d4 + k, reinterpret_cast<const int4*>(src)[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < W; ++k) __stcs(dst + k, src[k]);
+  }
+}
+
+// Coalesced tile output for the streaming kernels: the CTA's threads park their result rows
+// (W reals each) in shared memory and the CTA then writes the tile as one contiguous span with
+// 16-byte stores - every 128-byte line leaves the SM whole.  Rows are laid out with an odd stride
+// (in 16-byte units), which makes both the per-thread staging stores and the flat copy-out
+// reads bank-conflict free.  `ld` = reals between consecutive rows in global memory, `col0` =
+// first column (fk_all_links writes one 16-real block per link into 16*ndof-real rows).
+template <typename real, int W>
+struct RowStage {
+  static constexpr int PER = 16 / sizeof(real);
+  static constexpr bool kVec = (W % PER) == 0;
+  static constexpr int UNITS = kVec ? W / PER : W;
+  static constexpr int STRIDE = (UNITS % 2) ? UNITS : UNITS + 1;
+  static constexpr size_t kBytes = (size_t)kTile * STRIDE * (kVec ? 16 : sizeof(real));
+};
+
+template <typename real, int W>
+__device__ __forceinline__ void stage_store_rows(unsigned char* smem, const real* row,
+                                                 real* __restrict__ out, int64_t row0, int64_t n,
+                                                 int64_t ld, int64_t col0, bool vec) {
+  using RS = RowStage<real, W>;
+  const int t = threadIdx.x;
+  const int64_t left = n - row0;
+  const int rows = left < kTile ? (int)left : kTile;
+  if (RS::kVec && vec) {
+    int4* s = reinterpret_cast<int4*>(smem);
+#pragma unroll
+    for (int k = 0; k < RS::UNITS; ++k)
+      s[t * RS::STRIDE + k] = reinterpret_cast<const int4*>(row)[k];
+    __syncthreads();
+    const int total = rows * RS::UNITS;
+    for (int e = t; e < total; e += kTile) {
+      const int r = e / RS::UNITS, c = e - r * RS::UNITS;
+      __stcs(reinterpret_cast<int4*>(out + (row0 + r) * ld + col0) + c, s[r * RS::STRIDE + c]);
+    }
+  } else {
+    constexpr int SS = W | 1;
+    real* s = reinterpret_cast<real*>(smem);
+#pragma unroll
+    for (int k = 0; k < W; ++k) s[t * SS + k] = row[k];
+    __syncthreads();
+    const int total = rows * W;
+    for (int e = t; e < total; e += kTile) {
+      const int r = e / W, c = e - r * W;
+      __stcs(out + (row0 + r) * ld + col0 + c, s[r * SS + c]);
+    }
+  }
+}
+
+template <typename real, int W>
+constexpr size_t row_stage_bytes() {
+  return RowStage<real, W>::kBytes > (size_t)kTile * (W | 1) * sizeof(real)
+             ? RowStage<real, W>::kBytes
+             : (size_t)kTile * (W | 1) * sizeof(real);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// joint vector of configuration idx (AoS: one row; SoA: NDOF coalesced loads)
+template <typename real, int NDOF>
+__device__ __forceinline__ void load_q_direct(real* qv, const real* __restrict__ q, int64_t idx,
+                                              int64_t n, int layout, bool vec) {
+  if (idx < n) {
+    if (layout == ACRO_Q_AOS) {
+      alignas(16) real tmp[NDOF % 2 ? NDOF + 1 : NDOF];
+      load_row<real, NDOF>(tmp, q + idx * NDOF, vec);
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) qv[i] = tmp[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) qv[i] = __ldg(q + (int64_t)i * n + idx);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) qv[i] = real(0);
   }
 }
 

@@ -5,15 +5,13 @@
 // LinkKinematics.get_link_relative_transform (src/acrobotics/link.py:35-58).
 //
 // One thread per configuration, transform chained in registers.  HBM bound
-// (48 B in, 128 B out per configuration for a 6-dof fk): both the joint rows
-// and the 4x4 results cross global memory as flat coalesced blocks staged
-// through shared memory (a 16-double row per thread would otherwise be a
-// 128-byte-strided store).
+// (48 B in, 128 B out per configuration for a 6-dof fk): joint rows are read
+// with 16-byte loads, the 4x4 results leave through a bank-conflict-free
+// shared-memory tile as whole 128-byte lines (a 16-double row per thread
+// written directly would be a 128-byte-strided store of 16-byte pieces).
 #include "acro_launch.h"
 
 namespace acro {
-
-constexpr int kOutPad = 17;  // 16 reals + 1 pad: conflict-free staging rows
 
 template <typename real>
 __device__ __forceinline__ void stage_tf(real* row, const Tf<real>& T) {
@@ -30,43 +28,29 @@ __device__ __forceinline__ void stage_tf(real* row, const Tf<real>& T) {
   row[15] = real(1);
 }
 
-// copy the staged 16-real rows of this CTA out to global memory; consecutive
-// threads write consecutive reals, `row_stride` reals between configurations
-template <typename real>
-__device__ __forceinline__ void flush_tile(real* __restrict__ out, const real* s_out,
-                                           int64_t row0, int64_t n, int64_t row_stride,
-                                           int64_t col0) {
-  const int64_t left = n - row0;
-  const int rows = left < kTile ? (int)left : kTile;
-  for (int k = threadIdx.x; k < rows * 16; k += blockDim.x) {
-    const int r = k >> 4, c = k & 15;
-    out[(row0 + r) * row_stride + col0 + c] = s_out[r * kOutPad + c];
-  }
-}
-
+// Every thread reads its joint row with 16-byte loads (a warp covers one contiguous span);
+// results leave through a shared-memory tile as whole 128-byte lines (stage_store_rows).
 template <typename real, int NDOF, bool ALL>
 __global__ void __launch_bounds__(kTile)
     fk_kernel(const __grid_constant__ RobotDev<real> rb, const real* __restrict__ q, int64_t n,
-              int layout, real* __restrict__ out) {
+              int layout, real* __restrict__ out, bool vec_in, bool vec_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* s_q = reinterpret_cast<real*>(smem_raw);
-  real* s_out = s_q + kTile * NDOF;
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
-
+  const int64_t idx = row0 + threadIdx.x;
   real qv[NDOF];
-  load_q<real, NDOF>(qv, s_q, q, row0, n, layout);
+  load_q_direct<real, NDOF>(qv, q, idx, n, layout, vec_in);
 
   Tf<real> T;
   tf_load<real>(T, rb.base);
-  real* my_row = s_out + threadIdx.x * kOutPad;
+  alignas(16) real row[16];
 #pragma unroll
   for (int i = 0; i < NDOF; ++i) {
     chain_step<real>(T, rb, i, qv[i]);
     if (ALL) {
-      stage_tf<real>(my_row, T);
-      __syncthreads();
-      flush_tile<real>(out, s_out, row0, n, (int64_t)NDOF * 16, (int64_t)i * 16);
-      __syncthreads();
+      stage_tf<real>(row, T);
+      if (i > 0) __syncthreads();  // previous link's tile has left shared memory
+      stage_store_rows<real, 16>(smem_raw, row, out, row0, n, (int64_t)NDOF * 16, (int64_t)i * 16,
+                                 vec_out);
     }
   }
   if (!ALL) {
@@ -75,22 +59,20 @@ __global__ void __launch_bounds__(kTile)
       tf_mul<real>(E, T, rb.tip);
       T = E;
     }
-    stage_tf<real>(my_row, T);
-    __syncthreads();
-    flush_tile<real>(out, s_out, row0, n, 16, 0);
+    stage_tf<real>(row, T);
+    stage_store_rows<real, 16>(smem_raw, row, out, row0, n, 16, 0, vec_out);
   }
 }
 
 template <int NDOF>
 __global__ void __launch_bounds__(kTile)
     fk_rpy_kernel(const __grid_constant__ RobotDev<double> rb, const double* __restrict__ q,
-                  int64_t n, int layout, double* __restrict__ out) {
+                  int64_t n, int layout, double* __restrict__ out, bool vec_in, bool vec_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_q = reinterpret_cast<double*>(smem_raw);
-  double* s_out = s_q + kTile * NDOF;
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
   double qv[NDOF];
-  load_q<double, NDOF>(qv, s_q, q, row0, n, layout);
+  load_q_direct<double, NDOF>(qv, q, idx, n, layout, vec_in);
   Tf<double> T;
   tf_load<double>(T, rb.base);
 #pragma unroll
@@ -102,20 +84,14 @@ __global__ void __launch_bounds__(kTile)
   }
   // robot.py:73-77 (r_z uses T[0,1] and T[2,2]: the reference's own formula)
   const double s = sqrt(T.r[0] * T.r[0] + T.r[1] * T.r[1]);
-  double* row = s_out + threadIdx.x * 7;
+  alignas(16) double row[6];
   row[0] = T.p[0];
   row[1] = T.p[1];
   row[2] = T.p[2];
   row[3] = atan2(-T.r[5], T.r[8]);
   row[4] = atan2(T.r[2], s);
   row[5] = atan2(-T.r[1], T.r[8]);
-  __syncthreads();
-  const int64_t left = n - row0;
-  const int rows = left < kTile ? (int)left : kTile;
-  for (int k = threadIdx.x; k < rows * 6; k += blockDim.x) {
-    const int r = k / 6, c = k - 6 * r;
-    out[(row0 + r) * 6 + c] = s_out[r * 7 + c];
-  }
+  stage_store_rows<double, 6>(smem_raw, row, out, row0, n, 6, 0, vec_out);
 }
 
 template <typename real>
@@ -125,11 +101,12 @@ cudaError_t launch_fk(const RobotDev<real>& rb, const real* q, int64_t n, int la
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
   ACRO_DISPATCH_NDOF(rb.ndof, {
-    const size_t smem = sizeof(real) * (kTile * NDOF + kTile * kOutPad);
+    const bool vi = aligned16(q), vo = aligned16(out);
+    const size_t smem = row_stage_bytes<real, 16>();
     if (all_links)
-      fk_kernel<real, NDOF, true><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, out);
+      fk_kernel<real, NDOF, true><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, out, vi, vo);
     else
-      fk_kernel<real, NDOF, false><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, out);
+      fk_kernel<real, NDOF, false><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, out, vi, vo);
   });
   count_launch();
   return cudaGetLastError();
@@ -146,8 +123,8 @@ cudaError_t launch_fk_rpy(const RobotDev<double>& rb, const double* q, int64_t n
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
   ACRO_DISPATCH_NDOF(rb.ndof, {
-    const size_t smem = sizeof(double) * (kTile * NDOF + kTile * 7);
-    fk_rpy_kernel<NDOF><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, out);
+    fk_rpy_kernel<NDOF><<<(unsigned)tiles, kTile, row_stage_bytes<double, 6>(), st>>>(rb, q, n, layout, out, aligned16(q),
+                                                            aligned16(out));
   });
   count_launch();
   return cudaGetLastError();

@@ -47,16 +47,14 @@ __device__ __forceinline__ void fetch_rows(double* s_rows, const double* __restr
 template <int NDOF, bool RPY>
 __global__ void __launch_bounds__(kTile)
     jac_kernel(const __grid_constant__ RobotDev<double> rb, const double* __restrict__ q,
-               int64_t n, int layout, double* __restrict__ J) {
+               int64_t n, int layout, double* __restrict__ J, bool vec_in, bool vec_out) {
   constexpr int ROWS = RPY ? 6 : 3;
   constexpr int W = ROWS * NDOF;
-  constexpr int WP = W | 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_q = reinterpret_cast<double*>(smem_raw);
-  double* s_out = s_q + kTile * NDOF;
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  const int64_t idx = row0 + threadIdx.x;
   double qv[NDOF];
-  load_q<double, NDOF>(qv, s_q, q, row0, n, layout);
+  load_q_direct<double, NDOF>(qv, q, idx, n, layout, vec_in);
 
   // joint axis z_{i-1} and origin o_{i-1} are read off the frame *before* link i
   double z[NDOF][3], o[NDOF][3];
@@ -73,7 +71,7 @@ __global__ void __launch_bounds__(kTile)
     tf_mul<double>(E, T, rb.tip);
     T = E;
   }
-  double* row = s_out + threadIdx.x * WP;
+  alignas(16) double row[W + (W & 1)];
   // angle terms of robot.py:138-144, differentiated by the chain rule
   const double T00 = T.r[0], T01 = T.r[1], T02 = T.r[2], T12 = T.r[5], T22 = T.r[8];
   const double s = sqrt(T00 * T00 + T01 * T01);
@@ -113,8 +111,7 @@ __global__ void __launch_bounds__(kTile)
       }
     }
   }
-  __syncthreads();
-  flush_rows<W>(J, s_out, row0, n);
+  stage_store_rows<double, W>(smem_raw, row, J, row0, n, W, 0, vec_out);
 }
 
 cudaError_t launch_jac(const RobotDev<double>& rb, const double* q, int64_t n, int layout,
@@ -122,16 +119,17 @@ cudaError_t launch_jac(const RobotDev<double>& rb, const double* q, int64_t n, i
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const bool vi = aligned16(q), vo = aligned16(J);
   ACRO_DISPATCH_NDOF(rb.ndof, {
     if (rpy) {
-      const size_t smem = sizeof(double) * (kTile * NDOF + kTile * ((6 * NDOF) | 1));
+      const size_t smem = row_stage_bytes<double, 6 * NDOF>();
       auto k = jac_kernel<NDOF, true>;
       if (smem > 48 * 1024)
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, J);
+      k<<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, J, vi, vo);
     } else {
-      const size_t smem = sizeof(double) * (kTile * NDOF + kTile * ((3 * NDOF) | 1));
-      jac_kernel<NDOF, false><<<(unsigned)tiles, kTile, smem, st>>>(rb, q, n, layout, J);
+      jac_kernel<NDOF, false><<<(unsigned)tiles, kTile, row_stage_bytes<double, 3 * NDOF>(), st>>>(
+          rb, q, n, layout, J, vi, vo);
     }
   });
   count_launch();
@@ -304,29 +302,26 @@ template <bool WITH_CC>
 __global__ void __launch_bounds__(kTile)
     ik_kuka_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
                    const double* __restrict__ T, int64_t n, double* __restrict__ q_out,
-                   uint8_t* __restrict__ valid, uint8_t* __restrict__ free_mask) {
+                   uint8_t* __restrict__ valid, uint8_t* __restrict__ free_mask, bool vec_in,
+                   bool vec_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_rows = reinterpret_cast<double*>(smem_raw);  // 128 x 49 doubles
-  double* s_scene = s_rows + kTile * 49;
+  double* s_scene = reinterpret_cast<double*>(smem_raw + row_stage_bytes<double, 48>());
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   const int64_t idx = row0 + threadIdx.x;
-  if (WITH_CC)
+  if (WITH_CC) {
     for (int k = threadIdx.x; k < sc.n * kSceneStride; k += blockDim.x) s_scene[k] = sc.boxes[k];
-  fetch_rows<16>(s_rows, T, row0, n);
-  __syncthreads();
-  double Tin[16];
+    __syncthreads();
+  }
+  alignas(16) double Tin[16];
+  if (idx < n) {
+    load_row<double, 16>(Tin, T + idx * 16, vec_in);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 12; ++k) Tin[k] = idx < n ? s_rows[threadIdx.x * 17 + k] : (k % 5 == 0);
-  __syncthreads();
-  double sol[8][6];
+    for (int k = 0; k < 16; ++k) Tin[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  }
+  alignas(16) double sol[8][6];
   const unsigned vbits = kuka_ik(rb, Tin, sol);
-  double* row = s_rows + threadIdx.x * 49;
-#pragma unroll
-  for (int sl = 0; sl < 8; ++sl)
-#pragma unroll
-    for (int e = 0; e < 6; ++e) row[sl * 6 + e] = sol[sl][e];
-  __syncthreads();
-  flush_rows<48>(q_out, s_rows, row0, n);
+  stage_store_rows<double, 48>(smem_raw, &sol[0][0], q_out, row0, n, 48, 0, vec_out);
   if (idx < n) valid[idx] = (uint8_t)vbits;
   if (WITH_CC) {
     unsigned freebits = 0;
@@ -348,11 +343,11 @@ cudaError_t launch_ik_kuka(const RobotDev<double>& rb, const double* T, int64_t 
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(double) * kTile * 49;
+  const size_t smem = row_stage_bytes<double, 48>();
   auto k = ik_kuka_kernel<false>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<(unsigned)tiles, kTile, smem, st>>>(rb, SceneView<double>{nullptr, 0}, T, n, q_out, valid,
-                                          nullptr);
+                                          nullptr, aligned16(T), aligned16(q_out));
   count_launch();
   return cudaGetLastError();
 }
@@ -363,10 +358,11 @@ cudaError_t launch_ik_kuka_cc(const RobotDev<double>& rb, SceneView<double> sc, 
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(double) * (kTile * 49 + sc.n * kSceneStride);
+  const size_t smem = row_stage_bytes<double, 48>() + sizeof(double) * (sc.n * kSceneStride);
   auto k = ik_kuka_kernel<true>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<(unsigned)tiles, kTile, smem, st>>>(rb, sc, T, n, q_out, valid, free_mask);
+  k<<<(unsigned)tiles, kTile, smem, st>>>(rb, sc, T, n, q_out, valid, free_mask, aligned16(T),
+                                          aligned16(q_out));
   count_launch();
   return cudaGetLastError();
 }
