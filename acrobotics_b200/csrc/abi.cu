@@ -270,6 +270,7 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   p->view.dim = p->dim;
   p->view.delta = round_up_to_float(delta);
   p->view.q_lin_max = (float)robot->q_lin_max;
+  p->view.skip_nan = 0;
   cudaError_t e = cudaSuccess;
   if (scene->n > 0 && p->n_classes > 0) {
     const size_t cells = (size_t)p->dim * p->dim * p->dim * p->n_classes;
@@ -326,9 +327,10 @@ void build_cull_table(const double* packed, int n, CullTable& ct) {
 constexpr int64_t kFilterMinBatch = 4096;  // below this the plain FP64 kernel is used
 
 cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
-                          int64_t n, int layout, uint32_t* mask, cudaStream_t st) {
+                          int64_t n, int layout, uint32_t* mask, cudaStream_t st,
+                          bool skip_nan = false) {
   const int variant = k2_variant();
-  if (variant == 3 && n >= kFilterMinBatch) {
+  if ((variant == 3 || skip_nan) && n >= kFilterMinBatch) {
     static const AcroScene empty_scene{};
     const AcroScene* sc = scene ? scene : &empty_scene;
     const CullPlan* plan = nullptr;
@@ -348,7 +350,9 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
     uint32_t* amb = nullptr;
     e = cudaMallocAsync(&amb, sizeof(uint32_t) * ((n + 31) / 32), st);
     if (e != cudaSuccess) return e;
-    e = launch_fk_cc_filter(robot->d32, robot->d64, plan->view, plan->mask_bits,
+    GridView view = plan->view;
+    view.skip_nan = skip_nan ? 1 : 0;
+    e = launch_fk_cc_filter(robot->d32, robot->d64, view, plan->mask_bits,
                             view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
                             amb, st);
     cudaError_t e2 = cudaFreeAsync(amb, st);
@@ -688,9 +692,26 @@ int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const do
   if (int rc = check_kuka(robot)) return rc;
   if (int rc = check_batch(robot, T, q_out, n)) return rc;
   if (n > 0 && (!valid || !free_mask)) return fail(ACRO_E_INVALID, "valid/free_mask is NULL");
-  return finish(launch_ik_kuka_cc(robot->d64, view_of<double>(scene), T, n, q_out, valid,
-                                  free_mask, as_stream(stream)),
-                "acro_ik_kuka_cc_f64");
+  cudaStream_t st = as_stream(stream);
+  if (8 * n < kFilterMinBatch)
+    return finish(launch_ik_kuka_cc(robot->d64, view_of<double>(scene), T, n, q_out, valid,
+                                    free_mask, st),
+                  "acro_ik_kuka_cc_f64");
+  // large batches: IK kernel, then the filtered K2 kernel over the (8n, 6) solution rows
+  // (absent branches are NaN rows and are skipped), then free = valid & ~hit.  Configuration
+  // 8*i + s is bit s of byte i of the K2 mask, so the mask bytes line up with `valid`.
+  cudaError_t e = launch_ik_kuka(robot->d64, T, n, q_out, valid, st);
+  uint32_t* hit = nullptr;
+  if (e == cudaSuccess) e = cudaMallocAsync(&hit, sizeof(uint32_t) * ((8 * n + 31) / 32), st);
+  if (e == cudaSuccess)
+    e = run_fk_cc_f64(robot, scene, q_out, 8 * n, ACRO_Q_AOS, hit, st, /*skip_nan=*/true);
+  if (e == cudaSuccess)
+    e = launch_free_mask(valid, reinterpret_cast<const uint8_t*>(hit), n, free_mask, st);
+  if (hit) {
+    cudaError_t e2 = cudaFreeAsync(hit, st);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_ik_kuka_cc_f64");
 }
 
 int acro_ik_arm2_f64(double a1, double a2, double a3, const double* p, int64_t n, double* q_out,

@@ -91,6 +91,7 @@ struct GridView {
   int32_t dim;
   float delta;        // FP32 filter tolerance (bound on |s_fp32 - s_fp64| of any SAT quantity)
   float q_lin_max;    // prismatic joint travel covered by the bound
+  int32_t skip_nan;   // rows holding NaN are absent IK branches: not evaluated, verdict bit 0
 };
 
 // ---------------------------------------------------------------------------

@@ -52,6 +52,9 @@ cudaError_t launch_ik_kuka(const RobotDev<double>& rb, const double* T, int64_t 
 cudaError_t launch_ik_kuka_cc(const RobotDev<double>& rb, SceneView<double> sc, const double* T,
                               int64_t n, double* q_out, uint8_t* valid, uint8_t* free_mask,
                               cudaStream_t st);
+// free[i] = valid[i] & ~hit[i]  (bytes: the eight IK branches of pose i)
+cudaError_t launch_free_mask(const uint8_t* valid, const uint8_t* hit, int64_t n, uint8_t* free_mask,
+                             cudaStream_t st);
 cudaError_t launch_ik_arm2(double a1, double a2, double a3, const double* p, int64_t n,
                            double* q_out, uint8_t* valid, cudaStream_t st);
 cudaError_t launch_ik_anthro(double l2, double l3, const double* p, int64_t n, double* q_out,

@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
         // joint values the FP32 chain cannot follow within its error bound
         const double lim = prismatic ? (double)grid.q_lin_max : 1.0e8;
         if (!done && !(fabs(qi) <= lim)) {
-          amb = true;
-          done = true;  // decided by the FP64 pass
+          amb = !(grid.skip_nan && qi != qi);
+          done = true;  // decided by the FP64 pass (or an absent IK branch)
           qi = 0.0;
         }
         float s, c;

@@ -45,7 +45,7 @@ __device__ __forceinline__ void fetch_rows(double* s_rows, const double* __restr
 // Jacobians
 // ---------------------------------------------------------------------------
 template <int NDOF, bool RPY>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, RPY ? 4 : 5)
     jac_kernel(const __grid_constant__ RobotDev<double> rb, const double* __restrict__ q,
                int64_t n, int layout, double* __restrict__ J, bool vec_in, bool vec_out) {
   constexpr int ROWS = RPY ? 6 : 3;
@@ -363,6 +363,21 @@ cudaError_t launch_ik_kuka_cc(const RobotDev<double>& rb, SceneView<double> sc, 
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<(unsigned)tiles, kTile, smem, st>>>(rb, sc, T, n, q_out, valid, free_mask, aligned16(T),
                                           aligned16(q_out));
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+    free_mask_kernel(const uint8_t* __restrict__ valid, const uint8_t* __restrict__ hit, int64_t n,
+                     uint8_t* __restrict__ free_mask) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) free_mask[i] = valid[i] & (uint8_t)~hit[i];
+}
+
+cudaError_t launch_free_mask(const uint8_t* valid, const uint8_t* hit, int64_t n, uint8_t* free_mask,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  free_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(valid, hit, n, free_mask);
   count_launch();
   return cudaGetLastError();
 }

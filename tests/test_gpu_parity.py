@@ -318,6 +318,16 @@ def test_ik_fused_collision_filter(gpu):
     gq = no.collision_margins(spec(k), scene, flat[:20_000])
     robust = np.abs(gq) > MARGIN
     assert (hit[:20_000][robust] == ~(gq[robust] > 0)).all()
+    # unreachable poses (absent branches) mixed in; the small-batch kernel (one fused launch)
+    # and the large-batch pipeline (IK kernel -> filtered K2 -> mask combine) agree
+    T2 = T[:4001].copy()
+    T2[::5, :3, 3] *= 3.0
+    sol_a, valid_a, free_a = k.ik_filtered_batch(T2, scene)
+    assert (valid_a[::5] == False).any() and valid_a.any()  # noqa: E712
+    assert not free_a[~valid_a].any()
+    for lo in range(0, 4001, 500):
+        sol_b, valid_b, free_b = k.ik_filtered_batch(T2[lo:lo + 500], scene)
+        assert (valid_b == valid_a[lo:lo + 500]).all() and (free_b == free_a[lo:lo + 500]).all()
 
 
 def test_kuka_on_rail_ik(gpu):
