@@ -741,9 +741,27 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
   if (int rc = check_batch(robot, q_start, mask, n_segments)) return rc;
   if (n_segments > 0 && !q_goal) return fail(ACRO_E_INVALID, "q_goal is NULL");
   if (!(max_q_step > 0.0)) return fail(ACRO_E_INVALID, "max_q_step must be > 0");
-  return finish(launch_path_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_segments,
-                               max_q_step, mask, as_stream(stream)),
-                "acro_path_cc_f64");
+  cudaStream_t st = as_stream(stream);
+  if (k2_variant() != 3 || n_segments < 1024)
+    return finish(launch_path_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_segments,
+                                 max_q_step, mask, st),
+                  "acro_path_cc_f64");
+  static const AcroScene empty_scene{};
+  const CullPlan* plan = nullptr;
+  cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
+  if (e != cudaSuccess) return finish(e, "acro_path_cc_f64");
+  const int64_t n_words = (n_segments + 31) / 32;
+  void* scratch = nullptr;
+  e = cudaMallocAsync(&scratch, ((sizeof(uint32_t) * n_words + 7) / 8) * 8 + 8, st);
+  if (e == cudaSuccess)
+    e = launch_path_cc_filter(robot->d32, robot->d64, plan->view, plan->mask_bits,
+                              view_of<float>(scene), view_of<double>(scene), q_start, q_goal,
+                              n_segments, max_q_step, mask, scratch, st);
+  if (scratch) {
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_path_cc_f64");
 }
 
 int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms) {

@@ -66,6 +66,14 @@ cudaError_t launch_path_cc(const RobotDev<double>& rb, SceneView<double> sc, con
                            const double* q1, int64_t n_seg, double max_q_step, uint32_t* mask,
                            cudaStream_t st);
 
+// filtered sweep (FP32 filter + exact FP64 pass over the ambiguous segments); `scratch` holds
+// 8 * ceil(ceil(n_seg / 32) / 2) + 8 bytes
+cudaError_t launch_path_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
+                                  const GridView& grid, int mask_bits, SceneView<float> sc32,
+                                  SceneView<double> sc64, const double* q0, const double* q1,
+                                  int64_t n_seg, double max_q_step, uint32_t* mask,
+                                  void* scratch, cudaStream_t st);
+
 cudaError_t measure_fma_peak(bool fp64, int iters, double* tflops, double* ms);
 
 #define ACRO_DISPATCH_NDOF(ndof, ...)            \

@@ -115,3 +115,32 @@ def test_grid_resolution_does_not_change_verdicts(gpu):
             assert (k.is_in_collision_batch(q, scene16()) == ref).all()
     finally:
         _native.set_option("k2_grid", 96)
+
+
+def test_filtered_path_sweep_equals_fp64(gpu):
+    """K6: lane-refill filter kernel + FP64 pass over ambiguous segments == warp-per-segment
+    FP64 kernel, for short (planner edge), long, empty and mixed segments."""
+    k = ab.Kuka()
+    rng = np.random.default_rng(21)
+    n = 60_000
+    qs = rng.uniform(-np.pi, np.pi, (n, 6))
+    cases = {
+        "short": qs + rng.uniform(-0.15, 0.15, qs.shape),
+        "long": rng.uniform(-np.pi, np.pi, (n, 6)),
+        "mixed": np.where(rng.random((n, 1)) < 0.5, qs + rng.uniform(-0.05, 0.05, qs.shape),
+                          rng.uniform(-np.pi, np.pi, (n, 6))),
+    }
+    cases["mixed"][::97] = qs[::97]  # zero-length segments: empty path, never in collision
+    for name, qg in cases.items():
+        for scene, step in ((scene16(), 0.1), (readme_scene(), 0.25)):
+            call = lambda: k.is_path_in_collision_discrete_batch(qs, qg, scene, step)  # noqa: E731
+            ref = _with_variant("simple", call)
+            got = _with_variant("filter", call)
+            assert (got == ref).all(), f"{name}: {int((got != ref).sum())} segments differ"
+            if name == "mixed":
+                assert not got[::97].any()
+    # free space: a scene nobody touches -> nothing collides except through self collision
+    far = ab.Scene([ab.Box(1, 1, 1)], [translation(30, 0, 0)])
+    qg = qs + rng.uniform(-0.3, 0.3, qs.shape)
+    call = lambda: k.is_path_in_collision_discrete_batch(qs, qg, far, 0.1)  # noqa: E731
+    assert (_with_variant("simple", call) == _with_variant("filter", call)).all()
