@@ -714,6 +714,30 @@ int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const do
   return finish(e, "acro_ik_kuka_cc_f64");
 }
 
+int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene, const double* T,
+                                 int64_t n_points, int32_t samples_per_point, double* q_all,
+                                 uint8_t* valid, uint8_t* free_mask, double* q_free,
+                                 int64_t capacity, int64_t* offsets, void* stream) {
+  if (n_points < 0 || samples_per_point < 1) return fail(ACRO_E_INVALID, "bad point / sample count");
+  if (!offsets || capacity < 0 || (capacity > 0 && !q_free))
+    return fail(ACRO_E_INVALID, "offsets / q_free is NULL");
+  const int64_t n = n_points * samples_per_point;
+  if (int rc = acro_ik_kuka_cc_f64(robot, scene, T, n, q_all, valid, free_mask, stream)) return rc;
+  cudaStream_t st = as_stream(stream);
+  const size_t temp = n_points > 0 ? csr_temp_bytes(n_points) : 0;
+  void* scratch = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (n_points > 0) e = cudaMallocAsync(&scratch, sizeof(int64_t) * n_points + temp + 16, st);
+  if (e == cudaSuccess)
+    e = launch_csr_compact(q_all, free_mask, n_points, samples_per_point, offsets, q_free, capacity,
+                           scratch, temp, st);
+  if (scratch) {
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_joint_solutions_csr_f64");
+}
+
 int acro_ik_arm2_f64(double a1, double a2, double a3, const double* p, int64_t n, double* q_out,
                      uint8_t* valid, void* stream) {
   if (n < 0 || (n > 0 && (!p || !q_out || !valid))) return fail(ACRO_E_INVALID, "bad arguments");

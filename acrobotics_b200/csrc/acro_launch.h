@@ -74,6 +74,12 @@ cudaError_t launch_path_cc_filter(const RobotDev<float>& rb32, const RobotDev<do
                                   int64_t n_seg, double max_q_step, uint32_t* mask,
                                   void* scratch, cudaStream_t st);
 
+// CSR compaction of the collision-free IK solutions per path point (planner.cu)
+size_t csr_temp_bytes(int64_t n_points);
+cudaError_t launch_csr_compact(const double* q_all, const uint8_t* free_mask, int64_t n_points,
+                               int samples, int64_t* offsets, double* q_free, int64_t capacity,
+                               void* scratch, size_t temp_bytes, cudaStream_t st);
+
 cudaError_t measure_fma_peak(bool fp64, int iters, double* tflops, double* ms);
 
 #define ACRO_DISPATCH_NDOF(ndof, ...)            \

@@ -187,6 +187,21 @@ int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const do
                         int64_t n, double* q_out, uint8_t* valid, uint8_t* free_mask,
                         void* stream);
 
+/* ---- planner inner loop ------------------------------------------------------------
+ * PathPt.to_joint_solutions (path/path_pt_base.py:87-111) for n_points path points with
+ * samples_per_point sampled poses each (T is (n_points * samples_per_point, 4, 4), point
+ * major): IK of every pose, collision filter, and compaction of the surviving joint vectors
+ * into CSR form.  q_all (N,8,6), valid (N), free_mask (N) are the outputs of
+ * acro_ik_kuka_cc_f64 (kept: the caller may want them).  q_free receives up to `capacity`
+ * rows of 6 doubles; rows offsets[p] .. offsets[p+1]-1 belong to point p, in the reference's
+ * order (samples in order, each pose's solutions in Kuka.ik's order); offsets has
+ * n_points + 1 entries and offsets[n_points] is the total number of surviving solutions
+ * (rows beyond `capacity` are not written - compare the total with the capacity).      */
+int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene, const double* T,
+                                 int64_t n_points, int32_t samples_per_point, double* q_all,
+                                 uint8_t* valid, uint8_t* free_mask, double* q_free,
+                                 int64_t capacity, int64_t* offsets, void* stream);
+
 /* ---- K6: discretised path sweep -----------------------------------------------
  * Robot.is_path_in_collision_discrete (robot.py:229-237, :275-283) for E
  * segments: q_start/q_goal (E,ndof); mask bit e = some interpolant collides.    */

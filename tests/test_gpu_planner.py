@@ -1,0 +1,102 @@
+"""Planner inner loop (pose grid -> IK -> collision filter -> CSR) against the oracle."""
+import numpy as np
+import pytest
+from helpers import spec
+
+import acrobotics_b200 as ab
+from acrobotics_b200.path import (NoTolerance, SymmetricTolerance, TolEulerPt, TolPositionPt,
+                                  joint_solutions_csr, path_to_joint_solutions)
+from acrobotics_b200.synthetic import random_configs, scene16
+from oracle import np_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_csr(k, T, scene):
+    P, S = T.shape[:2]
+    s = spec(k)
+    sol, valid = no.ik_kuka(s, T.reshape(-1, 4, 4))
+    rows, offsets = [], [0]
+    margins = []
+    for p in range(P):
+        for i in range(p * S, (p + 1) * S):
+            for sl in range(8):
+                if valid[i, sl]:
+                    rows.append(sol[i, sl])
+        offsets.append(len(rows))
+    rows = np.array(rows).reshape(-1, 6)
+    g = no.collision_margins(s, scene, rows) if len(rows) else np.zeros(0)
+    return rows, np.array(offsets), g
+
+
+def test_csr_pipeline_matches_oracle(gpu):
+    k = ab.Kuka()
+    scene = scene16()
+    rng = np.random.default_rng(4)
+    P, S = 37, 50
+    q = random_configs(P * S, 6, seed=9)
+    T = k.fk_batch(q).reshape(P, S, 4, 4)
+    T[::6, ::3, :3, 3] *= 4.0  # some unreachable samples
+    q_free, off, q_all, valid, free = joint_solutions_csr(k, T, scene, return_all=True)
+    assert off.shape == (P + 1,) and off[0] == 0 and off[-1] == len(q_free)
+    rows, cand_off, g = _oracle_csr(k, T, scene)
+    robust = np.abs(g) > 1e-6
+    assert robust.mean() > 0.999
+    # expected survivors: candidates with g > 0, in order; compare per path point
+    keep = g > 0
+    for p in range(P):
+        lo, hi = cand_off[p], cand_off[p + 1]
+        exp = rows[lo:hi][keep[lo:hi]]
+        got = q_free[off[p]:off[p + 1]]
+        if robust[lo:hi].all():
+            assert got.shape == exp.shape, p
+            assert np.abs(got - exp).max(initial=0.0) <= 1e-9
+    # the CSR rows are exactly the free-flagged entries of q_all, in order
+    bits = np.unpackbits(free.reshape(-1, 1), axis=1, bitorder="little").astype(bool)
+    assert np.array_equal(q_all.reshape(-1, 8, 6)[bits], q_free)
+    assert not (free & ~valid).any()
+
+
+def test_csr_large_and_ragged(gpu):
+    k = ab.Kuka()
+    scene = scene16()
+    for P, S in ((1, 1), (3, 33), (2000, 7), (513, 64)):
+        q = random_configs(P * S, 6, seed=P)
+        T = k.fk_batch(q).reshape(P, S, 4, 4)
+        q_free, off, q_all, valid, free = joint_solutions_csr(k, T, scene, return_all=True)
+        counts = np.unpackbits(free.reshape(P, S, 1), axis=2, bitorder="little").sum(axis=(1, 2))
+        assert np.array_equal(np.diff(off), counts)
+        bits = np.unpackbits(free.reshape(-1, 1), axis=1, bitorder="little").astype(bool)
+        assert np.array_equal(q_all.reshape(-1, 8, 6)[bits], q_free)
+        # every surviving row is collision free and reproduces its pose
+        if len(q_free):
+            assert not k.is_in_collision_batch(q_free, scene).any()
+
+
+def test_path_points_to_joint_solutions(gpu):
+    """Welding-like line with a rotation tolerance about the tool axis
+    (reference tests/test_planning_sampling_based.py style set-up)."""
+    k = ab.Kuka()
+    scene = ab.Scene([ab.Box(0.5, 0.5, 0.1)], [np.array(
+        [[1, 0, 0, 0.8], [0, 1, 0, 0], [0, 0, 1, -0.1], [0, 0, 0, 1.0]])])
+    R = np.array([[1.0, 0, 0], [0, -1.0, 0], [0, 0, -1.0]])  # tool pointing down
+    path = [TolEulerPt([0.8, y, 0.2], R, [NoTolerance()] * 3,
+                       [NoTolerance(), NoTolerance(), SymmetricTolerance(np.pi, 12)])
+            for y in np.linspace(-0.2, 0.2, 15)]
+    path.append(TolPositionPt([0.8, 0.25, 0.2], R, [SymmetricTolerance(0.05, 3), NoTolerance(),
+                                                    NoTolerance()]))
+    Q = path_to_joint_solutions(path, k, scene)
+    assert len(Q) == len(path)
+    for pt, js in zip(path, Q):
+        assert js.ndim == 2 and js.shape[1] == 6 and len(js) > 0
+        assert not k.is_in_collision_batch(js, scene).any()
+        # each solution reproduces one of the sampled poses
+        Tq = k.fk_batch(js)
+        grid = pt.sample_grid_array()
+        err = np.abs(Tq[:, None] - grid[None]).max(axis=(2, 3)).min(axis=1)
+        assert err.max() < 1e-6
+        # single-point API agrees with the batched one
+    one = path[3].to_joint_solutions(k, None, scene)
+    assert np.array_equal(one, Q[3])
+    with pytest.raises(Exception):
+        path_to_joint_solutions([TolPositionPt([5.0, 0, 0], R, [NoTolerance()] * 3)], k, scene)
