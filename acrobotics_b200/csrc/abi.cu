@@ -192,14 +192,12 @@ int finish(cudaError_t e, const char* where) { return e == cudaSuccess ? 0 : cud
 float round_up_to_float(double x);
 
 // ACRO_K2_VARIANT selects the kernel behind the plain FP64 K2 path (A/B measurements,
-// cross-checks): "filter" (default, fk_cc_filt.cu), "wave" (fk_cc_wave.cu), "sm"
-// (fk_cc_sm.cu), "simple" (fk_cc.cu)
+// cross-checks): "filter" (default, fk_cc_filt.cu), "wave" (fk_cc_wave.cu), "simple" (fk_cc.cu)
 std::atomic<int> g_k2_variant{-1};
 std::atomic<int> g_grid_dim{-1};
 
 int parse_variant(const std::string& s) {
   if (s == "simple") return 2;
-  if (s == "sm") return 1;
   if (s == "wave") return 0;
   if (s == "filter") return 3;
   return -1;
@@ -361,8 +359,6 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
   if (variant == 2 || variant == 3 || (variant == 0 && !wave_supports(robot->d64)))
     return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, nullptr,
                                 0.0, st);
-  if (variant == 1)
-    return launch_fk_cc_sm(robot->d64, view_of<double>(scene), q, n, layout, mask, st);
   static const CullTable empty_table = {};
   return launch_fk_cc_wave(robot->d64, scene ? scene->cull : empty_table, view_of<double>(scene),
                            q, n, layout, mask, st);
@@ -398,7 +394,7 @@ int acro_set_option(const char* name, const char* value) {
   const std::string n(name), v(value);
   if (n == "k2_variant") {
     const int k = parse_variant(v);
-    if (k < 0) return fail(ACRO_E_INVALID, "k2_variant: filter | wave | sm | simple");
+    if (k < 0) return fail(ACRO_E_INVALID, "k2_variant: filter | wave | simple");
     g_k2_variant.store(k);
     return 0;
   }

@@ -22,11 +22,7 @@ cudaError_t launch_fk_cc(const RobotDev<real>& rb, SceneView<real> sc, const rea
                          int layout, uint32_t* mask, uint32_t* near_mask, real margin,
                          cudaStream_t st);
 
-// production K2 (state machine + refill + FP32 cull); FP64, no near-margin output
-cudaError_t launch_fk_cc_sm(const RobotDev<double>& rb, SceneView<double> sc, const double* q,
-                            int64_t n, int layout, uint32_t* mask, cudaStream_t st);
-
-// production K2 (link-by-link wavefronts over a shared-memory work list + FP32 cull)
+// all-FP64 K2 variant (link-by-link wavefronts over a shared-memory work list + FP32 cull)
 bool wave_supports(const RobotDev<double>& rb);
 cudaError_t launch_fk_cc_wave(const RobotDev<double>& rb, const CullTable& ct,
                               SceneView<double> sc, const double* q, int64_t n, int layout,

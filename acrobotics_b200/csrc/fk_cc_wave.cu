@@ -1,5 +1,5 @@
-// fk_cc_wave.cu - K2, production variant: fused FK -> collision organised as
-// link-by-link wavefronts over a shared-memory work list.
+// fk_cc_wave.cu - K2, all-FP64 variant ("wave"; the production kernel is fk_cc_filt.cu):
+// fused FK -> collision organised as link-by-link wavefronts over a shared-memory work list.
 //
 // Same contract and bit-identical verdicts as fk_cc.cu (reference
 // Robot.is_in_collision, src/acrobotics/robot.py:244-273 + :206-221,

@@ -214,8 +214,9 @@ def run_ours(args):
     n = args.configs
     words = (n + 31) // 32
     q = random_configs_device(n, 6, seed=1000 + rank)
-    mask = torch.zeros(words, dtype=torch.int32, device="cuda")
-    gathered = torch.zeros(world * words, dtype=torch.int32, device="cuda") if world > 1 else None
+    # the kernel writes its mask words straight into this rank's slice of the gather buffer
+    gathered = torch.zeros(world * words, dtype=torch.int32, device="cuda")
+    mask = gathered[rank * words:(rank + 1) * words]
     stream = torch.cuda.current_stream().cuda_stream
 
     def kernel():

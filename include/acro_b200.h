@@ -101,7 +101,7 @@ const char* acro_last_error(void);
 int acro_device_count(void);
 
 /* Tuning knobs (process wide; defaults are the production settings):
- *   "k2_variant" = "filter" (default) | "wave" | "sm" | "simple": kernel behind acro_fk_cc_f64
+ *   "k2_variant" = "filter" (default) | "wave" | "simple": kernel behind acro_fk_cc_f64
  *                  without a near mask; all variants return identical verdicts;
  *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 96).
  * The environment variables ACRO_K2_VARIANT / ACRO_K2_GRID set the initial values.    */

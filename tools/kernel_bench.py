@@ -171,6 +171,29 @@ def main():
         b, a = timed(f, args.reps)
         emit("fk_cc_f32[scene16]", b, a, n, 24.125, k2_extra(b))
 
+    if want("planner"):
+        # BASELINE config 5: 10k-point tolerance path x 400 pose samples x <= 8 IK branches
+        P, S = 10_000, 400
+        m = P * S
+        T = torch.empty((m, 4, 4), dtype=torch.float64, device="cuda")
+        _native.check(lib.acro_fk_f64(hk, q.data_ptr(), min(m, n), 0, T.data_ptr(), 0, stream))
+        if m > n:
+            T[n:] = T[: m - n]
+        q_all = torch.empty((m, 8, 6), dtype=torch.float64, device="cuda")
+        valid = torch.empty(m, dtype=torch.uint8, device="cuda")
+        free = torch.empty(m, dtype=torch.uint8, device="cuda")
+        q_free = torch.empty((8 * m, 6), dtype=torch.float64, device="cuda")
+        offsets = torch.zeros(P + 1, dtype=torch.int64, device="cuda")
+        f = lambda: _native.check(lib.acro_joint_solutions_csr_f64(  # noqa: E731
+            hfull, hs, T.data_ptr(), P, S, q_all.data_ptr(), valid.data_ptr(), free.data_ptr(),
+            q_free.data_ptr(), 8 * m, offsets.data_ptr(), stream))
+        b, a = timed(f, args.reps)
+        total = int(offsets[-1].item())
+        emit("joint_solutions_csr_f64[10k x 400]", b, a, m, None,
+             {"poses_per_s": m / (b * 1e-3), "ik_solutions_checked_per_s": 8 * m / (b * 1e-3),
+              "collision_free_solutions": total})
+        del T, q_all, q_free
+
     if want("path"):
         e = n // 16
         qs = q[:e].contiguous()
