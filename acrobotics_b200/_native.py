@@ -86,6 +86,7 @@ SIGNATURES = {
     "acro_ik_kuka_f64": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "acro_ik_kuka_cc_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
     "acro_joint_solutions_csr_f64": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I64, _P, _P]),
+    "acro_shortest_path_f64": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "acro_ik_arm2_f64": (C.c_int, [_D, _D, _D, _P, _I64, _P, _P, _P]),
     "acro_ik_anthropomorphic_f64": (C.c_int, [_D, _D, _P, _I64, _P, _P, _P]),
     "acro_ik_wrist_f64": (C.c_int, [_P, C.POINTER(_D), _I64, _P, _P]),

@@ -734,6 +734,28 @@ int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene,
   return finish(e, "acro_joint_solutions_csr_f64");
 }
 
+int acro_shortest_path_f64(const double* q, int32_t ndof, const int64_t* offsets_host,
+                           int64_t n_layers, int32_t cost_type, const double* weights_host,
+                           const double* state_cost, double* value_work, int32_t* pred_work,
+                           int64_t* offsets_work, int64_t* path_rows, double* length, void* stream) {
+  if (!offsets_host || n_layers < 1) return fail(ACRO_E_INVALID, "need at least one layer");
+  if (ndof < 1 || ndof > ACRO_MAX_DOF) return fail(ACRO_E_UNSUPPORTED, "ndof outside 1..ACRO_MAX_DOF");
+  if (cost_type < 0 || cost_type > 3) return fail(ACRO_E_INVALID, "unknown cost function");
+  if (cost_type == 3 && !weights_host) return fail(ACRO_E_INVALID, "weights are required");
+  if (!q || !value_work || !pred_work || !offsets_work || !path_rows || !length)
+    return fail(ACRO_E_INVALID, "NULL buffer");
+  for (int64_t l = 0; l < n_layers; ++l)
+    if (offsets_host[l + 1] <= offsets_host[l])
+      return fail(ACRO_E_INVALID, "empty layer: no path exists");  // success = False upstream
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemcpyAsync(offsets_work, offsets_host, sizeof(int64_t) * (n_layers + 1),
+                                  cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = launch_shortest_path(q, ndof, offsets_host, offsets_work, n_layers, cost_type, weights_host,
+                             state_cost, value_work, pred_work, path_rows, length, st);
+  return finish(e, "acro_shortest_path_f64");
+}
+
 int acro_ik_arm2_f64(double a1, double a2, double a3, const double* p, int64_t n, double* q_out,
                      uint8_t* valid, void* stream) {
   if (n < 0 || (n > 0 && (!p || !q_out || !valid))) return fail(ACRO_E_INVALID, "bad arguments");

@@ -76,6 +76,13 @@ cudaError_t launch_csr_compact(const double* q_all, const uint8_t* free_mask, in
                                int samples, int64_t* offsets, double* q_free, int64_t capacity,
                                void* scratch, size_t temp_bytes, cudaStream_t st);
 
+// layered-graph shortest path (dp.cu); cost_type: 0 l1, 1 l2, 2 sum squared, 3 weighted sum squared
+cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offsets_host,
+                                 const int64_t* offsets_dev, int64_t n_layers, int cost_type,
+                                 const double* weights_host, const double* state_cost,
+                                 double* value, int32_t* pred, int64_t* path_rows, double* length,
+                                 cudaStream_t st);
+
 cudaError_t measure_fma_peak(bool fp64, int iters, double* tflops, double* ms);
 
 #define ACRO_DISPATCH_NDOF(ndof, ...)            \

@@ -202,6 +202,18 @@ int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene,
                                  uint8_t* valid, uint8_t* free_mask, double* q_free,
                                  int64_t capacity, int64_t* offsets, void* stream);
 
+/* Shortest path through the layered graph of joint solutions (find_shortest_joint_path,
+ * planning/sampling_based.py:109-142 -> acrolib.dynamic_programming.shortest_path[_with_state_cost]).
+ * q (M, ndof) device rows in CSR order, offsets_host (n_layers + 1, HOST: one launch per layer
+ * is sized from it).  cost_type: 0 norm_l1, 1 norm_l2, 2 sum_squared, 3 weighted_sum_squared
+ * (weights_host: ndof doubles).  state_cost: M device doubles or NULL.  Work buffers (device):
+ * value_work M doubles, pred_work M int32, offsets_work n_layers + 1 int64.  Outputs (device):
+ * path_rows[l] = row of q chosen in layer l, *length = total cost.                        */
+int acro_shortest_path_f64(const double* q, int32_t ndof, const int64_t* offsets_host,
+                           int64_t n_layers, int32_t cost_type, const double* weights_host,
+                           const double* state_cost, double* value_work, int32_t* pred_work,
+                           int64_t* offsets_work, int64_t* path_rows, double* length, void* stream);
+
 /* ---- K6: discretised path sweep -----------------------------------------------
  * Robot.is_path_in_collision_discrete (robot.py:229-237, :275-283) for E
  * segments: q_start/q_goal (E,ndof); mask bit e = some interpolant collides.    */

@@ -100,3 +100,51 @@ def test_path_points_to_joint_solutions(gpu):
     assert np.array_equal(one, Q[3])
     with pytest.raises(Exception):
         path_to_joint_solutions([TolPositionPt([5.0, 0, 0], R, [NoTolerance()] * 3)], k, scene)
+
+
+@pytest.mark.parametrize("cost", ["norm_l1", "norm_l2", "sum_squared", "weighted_sum_squared"])
+def test_shortest_path_matches_cpu_dp(gpu, cost):
+    from acrobotics_b200.planning import find_shortest_joint_path, shortest_path
+    from oracle import dp_oracle
+
+    rng = np.random.default_rng(8)
+    sizes = [1, 7, 300, 33, 1000, 2, 64, 513]
+    layers = [rng.uniform(-3, 3, (n, 6)) for n in sizes]
+    w = np.array([1.0, 2.0, 0.5, 0.1, 3.0, 1.5]) if cost == "weighted_sum_squared" else None
+    ref = dp_oracle.shortest_path(layers, cost, w)
+    got = shortest_path(layers, cost, w)
+    assert got["success"] and abs(got["length"] - ref["length"]) <= 1e-9 * max(1, ref["length"])
+    assert np.array_equal(np.array(got["path"]), np.array(ref["path"]))
+    # with a state cost per node
+    sc = [rng.uniform(0, 2, n) for n in sizes]
+    ref = dp_oracle.shortest_path(layers, cost, w, sc)
+    got = shortest_path(layers, cost, w, sc)
+    assert abs(got["length"] - ref["length"]) <= 1e-9 * max(1, ref["length"])
+    assert np.array_equal(np.array(got["path"]), np.array(ref["path"]))
+    jp = find_shortest_joint_path(layers, cost, w)
+    assert len(jp.joint_positions) == len(sizes) and jp.cost > 0
+
+
+def test_shortest_path_edge_cases(gpu):
+    from acrobotics_b200.planning import find_shortest_joint_path, shortest_path
+
+    one = [np.array([[0.1, 0.2, 0.3]])]
+    res = shortest_path(one)
+    assert res["success"] and res["length"] == 0.0 and np.array_equal(res["path"][0], one[0][0])
+    # ties: identical nodes -> the lowest index is chosen, deterministic
+    layers = [np.zeros((5, 2)), np.ones((4, 2)), np.zeros((3, 2))]
+    res = shortest_path(layers, "norm_l1")
+    assert res["length"] == 4.0
+    assert shortest_path([np.zeros((2, 6)), np.zeros((0, 6))])["success"] is False
+    with pytest.raises(ValueError):
+        find_shortest_joint_path([np.zeros((2, 6)), np.zeros((0, 6))])
+    # a straight line in joint space is recovered exactly among distractors
+    rng = np.random.default_rng(1)
+    line = np.linspace([0, 0, 0, 0, 0, 0], [1, -1, 0.5, 0.2, 0, 2], 40)
+    layers = []
+    for p in line:
+        pts = p + rng.uniform(0.5, 2.0, (50, 6)) * rng.choice([-1, 1], (50, 6))
+        k = rng.integers(0, 51)
+        layers.append(np.insert(pts, k, p, axis=0))
+    res = shortest_path(layers, "sum_squared")
+    assert np.allclose(np.array(res["path"]), line)

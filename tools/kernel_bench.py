@@ -192,6 +192,23 @@ def main():
         emit("joint_solutions_csr_f64[10k x 400]", b, a, m, None,
              {"poses_per_s": m / (b * 1e-3), "ik_solutions_checked_per_s": 8 * m / (b * 1e-3),
               "collision_free_solutions": total})
+        # shortest path through the resulting layered graph (10k layers)
+        off_host = offsets.cpu().numpy().astype(np.int64)
+        if (np.diff(off_host) > 0).all():
+            M = int(off_host[-1])
+            value = torch.empty(M, dtype=torch.float64, device="cuda")
+            pred = torch.empty(M, dtype=torch.int32, device="cuda")
+            off_dev = torch.empty(P + 1, dtype=torch.int64, device="cuda")
+            rows = torch.empty(P, dtype=torch.int64, device="cuda")
+            length = torch.empty(1, dtype=torch.float64, device="cuda")
+            f = lambda: _native.check(lib.acro_shortest_path_f64(  # noqa: E731
+                q_free.data_ptr(), 6, off_host.ctypes.data, P, 2, None, None, value.data_ptr(),
+                pred.data_ptr(), off_dev.data_ptr(), rows.data_ptr(), length.data_ptr(), stream))
+            b, a = timed(f, max(2, args.reps // 2), warm=1)
+            edges = float((np.diff(off_host)[:-1].astype(np.float64) * np.diff(off_host)[1:]).sum())
+            emit("shortest_path_f64[10k layers]", b, a, M, None,
+                 {"edges": edges, "edges_per_s": edges / (b * 1e-3),
+                  "fp64_tflops": edges * 18 / (b * 1e-3) / 1e12, "length": float(length.item())})
         del T, q_all, q_free
 
     if want("path"):
