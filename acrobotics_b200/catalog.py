@@ -174,8 +174,8 @@ class Kuka(Robot):
         valid = closed_form_ik._bits_to_bool(bits, 8)
         return device.to_host(q, host), device.to_host(valid, host)
 
-    def ik_filtered_batch(self, T, scene):
-        """IK followed by the collision filter, fused in one kernel:
+    def ik_filtered_batch(self, T, scene, _force_self=False):
+        """IK followed by the collision filter (``scene=None``: self collision only):
         -> (q (N,8,6), valid (N,8), collision_free (N,8))."""
         Td, host = self._poses(T)
         n = Td.shape[0]
@@ -185,7 +185,8 @@ class Kuka(Robot):
         free = torch.empty(n, dtype=torch.uint8, device="cuda")
         _native.check(
             _native.load().acro_ik_kuka_cc_f64(
-                self._handle(), scene.native_handle() if scene is not None else None,
+                self._handle(force_self=_force_self),
+                scene.native_handle() if scene is not None else None,
                 Td.data_ptr(), n, q.data_ptr(), bits.data_ptr(), free.data_ptr(),
                 device.current_stream_ptr(),
             ),

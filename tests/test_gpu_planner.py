@@ -148,3 +148,39 @@ def test_shortest_path_edge_cases(gpu):
         layers.append(np.insert(pts, k, p, axis=0))
     res = shortest_path(layers, "sum_squared")
     assert np.allclose(np.array(res["path"]), line)
+
+
+def test_workspace_envelope(gpu):
+    """reference tests/test_workspace_envelope.py:16-23, :54-62 + consistency with the oracle."""
+    from acrobotics_b200.workspace_envelope import (EnvelopeSettings, calculate_reachability_batch,
+                                                    generate_positions, generate_robot_envelope,
+                                                    sample_position)
+
+    pos = np.array([0.1, 0.2, 0.3])
+    samples = sample_position(pos, 5, np.random.default_rng(1))
+    assert all(np.allclose(tf[:3, 3], pos) for tf in samples)
+    assert all(np.any(samples[i] != samples[i - 1]) for i in range(1, 5))
+    robot = ab.Kuka()
+    settings = EnvelopeSettings(1.0, 10, 8)
+    we = generate_robot_envelope(robot, settings, np.random.default_rng(2))
+    num_points = int(2 * robot.estimate_max_extension() / settings.sample_distance)
+    assert we.shape == (num_points ** 3, 4)
+    assert (we[:, 0] >= 0).all() and (we[:, 0] <= 1).all()
+    # against the oracle on a finer grid: same poses, IK + self collision on the CPU
+    pts = generate_positions(1.2, 5)
+    rng = np.random.default_rng(3)
+    got = calculate_reachability_batch(robot, pts, 20, 8, rng)
+    from acrobotics_b200.workspace_envelope import random_rotations
+    rng = np.random.default_rng(3)
+    T = np.tile(np.eye(4), (len(pts), 20, 1, 1))
+    T[:, :, :3, :3] = random_rotations(len(pts) * 20, rng).reshape(len(pts), 20, 3, 3)
+    T[:, :, :3, 3] = pts[:, None, :]
+    s = spec(robot)
+    sol, valid = no.ik_kuka(s, T.reshape(-1, 4, 4))
+    flat = sol[valid]
+    g = no.collision_margins(s, None, flat)
+    free = np.zeros(valid.shape, bool)
+    free[valid] = g > 0
+    exp = free.reshape(len(pts), -1).sum(axis=1) / (8 * 20)
+    assert np.abs(got - exp).max() <= 1.0 / 160 + 1e-12  # at most one near-contact solution
+    assert got.max() > 0.2 and got.min() == 0.0
