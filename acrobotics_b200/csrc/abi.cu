@@ -249,14 +249,15 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   p->dim = grid_dim_setting();
   p->mask_bits = scene->n <= 32 ? 32 : 64;
   p->cells = nullptr;
-  // FP32 filter tolerance: every SAT quantity is a sum of O(50) products of numbers
-  // bounded by the workspace size P; with unit roundoff 6e-8, sin/cos good to 1.2e-7 and six
-  // chained links the FP32 value stays within ~1e-5 P of the FP64 one.  Ten
-  // times that is used.
+  // FP32 filter tolerance.  Every SAT quantity is the result of O(100) FP32 operations on
+  // numbers bounded by the workspace size P (unit roundoff 6e-8, sin/cos good to 1.2e-7, six
+  // chained links): a first-order worst case is ~6e-6 P.  Measured over 4 M configurations x
+  // 96 pairs x 15 axes (acro_measure_filter_error, tests/test_gpu_k2_variants.py):
+  // 1.5e-6 for P = 4.5.  delta = 2e-5 P is 3x the crude bound and ~60x the measurement.
   const double base_norm = std::sqrt(p->centre[0] * p->centre[0] + p->centre[1] * p->centre[1] +
                                      p->centre[2] * p->centre[2]);
   const double P = base_norm + robot->reach + scene->bound;
-  const double delta = 1.0e-4 * std::max(1.0, P);
+  const double delta = 2.0e-5 * std::max(1.0, P);
   const double half = std::max(robot->reach, 1e-3);
   const double cell = 2.0 * half / p->dim;
   const double origin[3] = {p->centre[0] - half, p->centre[1] - half, p->centre[2] - half};
@@ -804,6 +805,25 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
     if (e == cudaSuccess) e = e2;
   }
   return finish(e, "acro_path_cc_f64");
+}
+
+int acro_filter_tolerance(const AcroRobot* robot, const AcroScene* scene, double* delta) {
+  if (!robot || !delta) return fail(ACRO_E_INVALID, "NULL argument");
+  static const AcroScene empty_scene{};
+  const CullPlan* plan = nullptr;
+  cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
+  if (e != cudaSuccess) return finish(e, "acro_filter_tolerance");
+  *delta = (double)plan->view.delta;
+  return 0;
+}
+
+int acro_measure_filter_error(const AcroRobot* robot, const AcroScene* scene, const double* q,
+                              int64_t n, double* out2, void* stream) {
+  if (int rc = check_batch(robot, q, out2, n)) return rc;
+  if (!scene) return fail(ACRO_E_INVALID, "scene handle is NULL");
+  return finish(launch_filter_error(robot->d32, robot->d64, view_of<float>(scene),
+                                    view_of<double>(scene), q, n, out2, as_stream(stream)),
+                "acro_measure_filter_error");
 }
 
 int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms) {

@@ -300,3 +300,109 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
 }
 
 }  // namespace acro
+
+// ---------------------------------------------------------------------------
+// measurement: how far are the filter's FP32 decision quantities from the FP64 ones?
+// ---------------------------------------------------------------------------
+namespace acro {
+
+// the 15 signed separations of FCL's test (face axes of box 2, of box 1, nine edge axes)
+template <typename real>
+__device__ __forceinline__ void sat_axes(const real* A, const real* R1, const real* c1,
+                                         const real* R2, const real* T2, const real* B,
+                                         real* s_out) {
+  const real p0 = T2[0] - c1[0], p1 = T2[1] - c1[1], p2 = T2[2] - c1[2];
+  real R[9], Q[9], pp[3];
+  for (int i = 0; i < 3; ++i) {
+    pp[i] = fma_t(R1[6 + i], p2, fma_t(R1[3 + i], p1, R1[i] * p0));
+    for (int j = 0; j < 3; ++j) {
+      R[3 * i + j] = fma_t(R1[6 + i], R2[6 + j], fma_t(R1[3 + i], R2[3 + j], R1[i] * R2[j]));
+      Q[3 * i + j] = abs_t(R[3 * i + j]);
+    }
+  }
+  for (int j = 0; j < 3; ++j) {
+    const real t = fma_t(R2[6 + j], p2, fma_t(R2[3 + j], p1, R2[j] * p0));
+    s_out[j] = abs_t(t) - (fma_t(Q[6 + j], A[2], fma_t(Q[3 + j], A[1], Q[j] * A[0])) + B[j]);
+  }
+  for (int i = 0; i < 3; ++i)
+    s_out[3 + i] = abs_t(pp[i]) -
+                   (fma_t(Q[3 * i + 2], B[2], fma_t(Q[3 * i + 1], B[1], Q[3 * i] * B[0])) + A[i]);
+  for (int k = 0; k < 9; ++k) Q[k] += real(1.0e-6);
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const real t = fma_t(pp[i2], R[3 * i1 + j], -(pp[i1] * R[3 * i2 + j]));
+      s_out[6 + 3 * i + j] =
+          abs_t(t) - fma_t(A[i1], Q[3 * i2 + j],
+                           fma_t(A[i2], Q[3 * i1 + j],
+                                 fma_t(B[j1], Q[3 * i + j2], B[j2] * Q[3 * i + j1])));
+    }
+  }
+}
+
+// out[0] = max over all (configuration, robot box, scene box, axis) of |s_fp32 - s_fp64|,
+// out[1] = max |box centre fp32 - fp64| (inf norm); the FP32 side uses exactly the filter's
+// arithmetic (sincos_filter + tf_mul_dh<float>), the FP64 side the exact kernels' chain_step.
+template <int NDOF>
+__global__ void __launch_bounds__(128)
+    filter_error_kernel(const __grid_constant__ RobotDev<float> rb32,
+                        const __grid_constant__ RobotDev<double> rb64, const SceneView<float> sc32,
+                        const SceneView<double> sc64, const double* __restrict__ q, int64_t n,
+                        double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  double worst_s = 0.0, worst_p = 0.0;
+  if (idx < n) {
+    Tf<float> Tf32;
+    Tf<double> Tf64;
+    tf_load<float>(Tf32, rb32.base);
+    tf_load<double>(Tf64, rb64.base);
+    for (int slot = 0; slot <= NDOF + 1; ++slot) {
+      if (slot >= 1 && slot <= NDOF) {
+        const int i = slot - 1;
+        const double qi = q[idx * NDOF + i];
+        const bool prismatic = (rb32.prismatic_mask >> i) & 1;
+        float s, c;
+        sincos_filter(prismatic ? (double)rb32.theta[i] : qi, s, c);
+        tf_mul_dh<float>(Tf32, c, s, rb32.ca[i], rb32.sa[i], rb32.a[i],
+                         prismatic ? (float)qi : rb32.d[i]);
+        chain_step<double>(Tf64, rb64, i, qi);
+      }
+      for (int b = rb32.slot_begin[slot]; b < rb32.slot_begin[slot + 1]; ++b) {
+        Tf<float> W32;
+        Tf<double> W64;
+        tf_mul<float>(W32, Tf32, rb32.boxes[b].off);
+        tf_mul<double>(W64, Tf64, rb64.boxes[b].off);
+        for (int k = 0; k < 3; ++k)
+          worst_p = fmax(worst_p, fabs((double)W32.p[k] - W64.p[k]));
+        for (int j = 0; j < sc64.n; ++j) {
+          const float* f = sc32.boxes + (size_t)j * kSceneStride;
+          const double* d = sc64.boxes + (size_t)j * kSceneStride;
+          float s32[15];
+          double s64[15];
+          sat_axes<float>(rb32.boxes[b].half, W32.r, W32.p, f, f + 9, f + 12, s32);
+          sat_axes<double>(rb64.boxes[b].half, W64.r, W64.p, d, d + 9, d + 12, s64);
+          for (int k = 0; k < 15; ++k) worst_s = fmax(worst_s, fabs((double)s32[k] - s64[k]));
+        }
+      }
+    }
+  }
+  // non-negative doubles order like their bit patterns
+  atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(worst_s));
+  atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(worst_p));
+}
+
+cudaError_t launch_filter_error(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
+                                SceneView<float> sc32, SceneView<double> sc64, const double* q,
+                                int64_t n, double* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess || n <= 0) return e;
+  ACRO_DISPATCH_NDOF(rb32.ndof, {
+    filter_error_kernel<NDOF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rb32, rb64, sc32, sc64, q,
+                                                                           n, out);
+  });
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace acro

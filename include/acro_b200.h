@@ -225,6 +225,14 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
  * DFMA / FFMA chain micro-benchmark: the compute-roofline denominator.  Returns
  * achieved TFLOP/s (FMA = 2 flop) in *tflops; runs on the current device.        */
 int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms);
+/* The filtered K2 kernel decides in FP32 with a tolerance delta.  These two
+ * calls expose the evidence: the tolerance used for a (robot, scene) pair, and the measured
+ * distance between the FP32 and FP64 decision quantities over a batch of configurations
+ * (device pointers; out2[0] = max |s_fp32 - s_fp64| over every configuration x robot box x
+ * scene box x axis, out2[1] = max error of a box centre).  Revolute joints within |q| <= 1e8. */
+int acro_filter_tolerance(const AcroRobot* robot, const AcroScene* scene, double* delta);
+int acro_measure_filter_error(const AcroRobot* robot, const AcroScene* scene, const double* q,
+                              int64_t n, double* out2, void* stream);
 /* counters of kernels launched by this library since load (all threads)          */
 int64_t acro_launch_count(void);
 

@@ -144,3 +144,30 @@ def test_filtered_path_sweep_equals_fp64(gpu):
     qg = qs + rng.uniform(-0.3, 0.3, qs.shape)
     call = lambda: k.is_path_in_collision_discrete_batch(qs, qg, far, 0.1)  # noqa: E731
     assert (_with_variant("simple", call) == _with_variant("filter", call)).all()
+
+
+def test_filter_tolerance_covers_measured_fp32_error(gpu):
+    """The filter is exact as long as |s_fp32 - s_fp64| <= delta for every SAT quantity.  Measure
+    the left-hand side over 4 M configurations x all link-box x scene-box pairs x 15 axes and
+    demand a factor 10 of head-room (typically it is ~60)."""
+    import ctypes
+
+    import torch
+
+    lib = _native.load()
+    for robot, ndof, scene, scale in ((ab.Kuka(), 6, scene16(), 1.0),
+                                      (ab.Kuka(), 6, scene16(seed=3, n_boxes=40), 1.0),
+                                      (ab.KukaOnRail(), 7, scene16(), 1.0),
+                                      (ab.Kuka(), 6, scene16(), 40.0)):
+        q = torch.from_numpy(random_configs(4_000_000 if ndof == 6 else 1_000_000, ndof, seed=31)
+                             * scale).cuda()
+        out = torch.zeros(2, dtype=torch.float64, device="cuda")
+        delta = ctypes.c_double()
+        _native.check(lib.acro_filter_tolerance(robot._handle(), scene.native_handle(),
+                                                ctypes.byref(delta)))
+        _native.check(lib.acro_measure_filter_error(robot._handle(), scene.native_handle(),
+                                                    q.data_ptr(), q.shape[0], out.data_ptr(), None))
+        worst_s, worst_p = out.cpu().tolist()
+        print(f"delta {delta.value:.3e}  max|s32-s64| {worst_s:.3e}  max centre error {worst_p:.3e}")
+        assert 0 < worst_s < delta.value / 10
+        assert worst_p < delta.value / 10
