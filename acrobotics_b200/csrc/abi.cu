@@ -329,7 +329,7 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
                           int64_t n, int layout, uint32_t* mask, cudaStream_t st,
                           bool skip_nan = false) {
   const int variant = k2_variant();
-  if ((variant == 3 || skip_nan) && n >= kFilterMinBatch) {
+  if ((variant >= 3 || skip_nan) && n >= kFilterMinBatch) {
     static const AcroScene empty_scene{};
     const AcroScene* sc = scene ? scene : &empty_scene;
     const CullPlan* plan = nullptr;
@@ -357,7 +357,7 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
     cudaError_t e2 = cudaFreeAsync(amb, st);
     return e != cudaSuccess ? e : e2;
   }
-  if (variant == 2 || variant == 3 || (variant == 0 && !wave_supports(robot->d64)))
+  if (variant >= 2 || (variant == 0 && !wave_supports(robot->d64)))
     return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, nullptr,
                                 0.0, st);
   static const CullTable empty_table = {};
@@ -785,7 +785,7 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
   if (n_segments > 0 && !q_goal) return fail(ACRO_E_INVALID, "q_goal is NULL");
   if (!(max_q_step > 0.0)) return fail(ACRO_E_INVALID, "max_q_step must be > 0");
   cudaStream_t st = as_stream(stream);
-  if (k2_variant() != 3 || n_segments < 1024)
+  if (k2_variant() < 3 || n_segments < 1024)
     return finish(launch_path_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_segments,
                                  max_q_step, mask, st),
                   "acro_path_cc_f64");

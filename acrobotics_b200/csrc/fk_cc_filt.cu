@@ -266,7 +266,6 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
   for (int b = 0; b < rb32.n_boxes; ++b)
     if (rb32.boxes[b].save_slot + 1 > n_saved) n_saved = rb32.boxes[b].save_slot + 1;
   if (!rb32.check_self) n_saved = 0;
-  const int64_t n_words = (n + 31) / 32;
   cudaError_t e = cudaSuccess;
   ACRO_DISPATCH_NDOF(rb32.ndof, {
     const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved);
@@ -290,6 +289,18 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+  });
+  if (e != cudaSuccess) return e;
+  return launch_fk_cc_fixup(rb64, sc64, q, n, layout, mask, amb_mask, st);
+}
+
+// exact FP64 pass over the configurations flagged in amb_mask
+cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> sc64, const double* q,
+                               int64_t n, int layout, uint32_t* mask, const uint32_t* amb_mask,
+                               cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t n_words = (n + 31) / 32;
+  ACRO_DISPATCH_NDOF(rb64.ndof, {
     const size_t fsmem = sizeof(double) * sc64.n * kSceneStride + sizeof(uint16_t) * kFixThreads * 32;
     const int64_t fblocks = (n_words + kFixThreads - 1) / kFixThreads;
     fk_cc_fixup_kernel<NDOF><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
