@@ -165,7 +165,8 @@ __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
 
 // One warp, 32 configurations (one per lane; `active` false = no configuration in this lane).
 // qfn(i) returns this lane's joint value i (double).  All 32 lanes must call it together.
-template <int NDOF, typename MaskT, typename QFn>
+// PRISM = false compiles the prismatic-joint handling out (rb.prismatic_mask must be 0).
+template <int NDOF, typename MaskT, bool PRISM, typename QFn>
 __device__ __forceinline__ void filter_chunk(const RobotDev<float>& rb, const GridView& grid,
                                              const FilterCtx& ctx, const unsigned lane,
                                              const bool active, QFn qfn, bool& hit, bool& amb) {
@@ -190,18 +191,23 @@ amb = false;
     if (slot >= 1 && slot <= ndof) {
       if (__all_sync(kFull, done)) break;
       const int i = slot - 1;
-      double qi = active ? qfn(i) : 0.0;
-      const bool prismatic = (rb.prismatic_mask >> i) & 1;
+      double qi = qfn(i);  // lanes without a configuration read an arbitrary (unused) value
+      const bool prismatic = PRISM && ((rb.prismatic_mask >> i) & 1);
       // joint values the FP32 chain cannot follow within its error bound
       const double lim = prismatic ? (double)grid.q_lin_max : 1.0e8;
       if (!done && !(fabs(qi) <= lim)) {
         amb = !(grid.skip_nan && qi != qi);
         done = true;  // decided by the FP64 pass (or an absent IK branch)
-        qi = 0.0;
       }
+      if (!(fabs(qi) <= lim)) qi = 0.0;
       float s, c;
-      sincos_filter(prismatic ? (double)rb.theta[i] : qi, s, c);
-      tf_mul_dh<float>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], prismatic ? (float)qi : rb.d[i]);
+      if (PRISM) {
+        sincos_filter(prismatic ? (double)rb.theta[i] : qi, s, c);
+        tf_mul_dh<float>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], prismatic ? (float)qi : rb.d[i]);
+      } else {
+        sincos_filter(qi, s, c);
+        tf_mul_dh<float>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], rb.d[i]);
+      }
     }
     for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
       const BoxDev<float>& bx = rb.boxes[b];

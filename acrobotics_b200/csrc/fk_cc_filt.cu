@@ -52,7 +52,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int NDOF, typename MaskT>
+template <int NDOF, typename MaskT, bool PRISM>
 __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved,
@@ -104,13 +104,13 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     prefetch(chunk + stride, buf ^ 1);
     cp_async_wait<1>();
     __syncwarp();
-    const double* my_q = s_q + buf * 32 * NDOF;
     const int64_t idx = (chunk << 5) + lane;
+    // this lane's joint i sits at qp[i * qs] (row of the flat AoS copy, or column of the SoA one)
+    const double* qp = s_q + buf * 32 * NDOF + (layout == ACRO_Q_AOS ? lane * NDOF : lane);
+    const int qs = layout == ACRO_Q_AOS ? 1 : 32;
     bool hit, amb;
-    filter_chunk<NDOF, MaskT>(
-        rb, grid, ctx, lane, idx < n,
-        [&](int i) { return layout == ACRO_Q_AOS ? my_q[lane * NDOF + i] : my_q[i * 32 + lane]; },
-        hit, amb);
+    filter_chunk<NDOF, MaskT, PRISM>(rb, grid, ctx, lane, idx < n,
+                                     [=](int i) { return qp[i * qs]; }, hit, amb);
 
     const unsigned word = __ballot_sync(kFull, hit);
     const unsigned aword = __ballot_sync(kFull, amb && !hit);
@@ -269,23 +269,25 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
   cudaError_t e = cudaSuccess;
   ACRO_DISPATCH_NDOF(rb32.ndof, {
     const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved);
-    if (mask_bits == 32) {
-      auto kern = fk_cc_filter_kernel<NDOF, uint32_t>;
-      if (smem > 48 * 1024)
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
+    auto launch = [&](auto kern) -> cudaError_t {
+      if (smem > 48 * 1024) {
+        cudaError_t e2 =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+      }
       const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
       kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, q, n, layout, mask,
                                                       amb_mask);
-    } else {
-      auto kern = fk_cc_filter_kernel<NDOF, uint64_t>;
-      if (smem > 48 * 1024)
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
-      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, q, n, layout, mask,
-                                                      amb_mask);
-    }
+      return cudaSuccess;
+    };
+    const bool prism = rb32.prismatic_mask != 0;
+    if (mask_bits == 32)
+      e = prism ? launch(fk_cc_filter_kernel<NDOF, uint32_t, true>)
+                : launch(fk_cc_filter_kernel<NDOF, uint32_t, false>);
+    else
+      e = prism ? launch(fk_cc_filter_kernel<NDOF, uint64_t, true>)
+                : launch(fk_cc_filter_kernel<NDOF, uint64_t, false>);
+    if (e != cudaSuccess) return e;
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
 
     const double s = path_param(k, n_steps, step);
     bool hit, amb;
-    filter_chunk<NDOF, MaskT>(
+    filter_chunk<NDOF, MaskT, true>(
         rb, grid, ctx, lane, active,
         [&](int i) { return (1.0 - s) * s_ab[i * 32 + lane] + s * s_ab[(NDOF + i) * 32 + lane]; },
         hit, amb);
