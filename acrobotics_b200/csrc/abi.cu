@@ -325,16 +325,23 @@ void build_cull_table(const double* packed, int n, CullTable& ct) {
 
 constexpr int64_t kFilterMinBatch = 4096;  // below this the plain FP64 kernel is used
 
+// near_mask != nullptr: margin mode (verdicts + the configurations within +-margin of contact)
 cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
                           int64_t n, int layout, uint32_t* mask, cudaStream_t st,
-                          bool skip_nan = false) {
+                          bool skip_nan = false, uint32_t* near_mask = nullptr,
+                          double margin = 0.0) {
   const int variant = k2_variant();
-  if ((variant >= 3 || skip_nan) && n >= kFilterMinBatch) {
-    static const AcroScene empty_scene{};
-    const AcroScene* sc = scene ? scene : &empty_scene;
-    const CullPlan* plan = nullptr;
-    cudaError_t e = get_plan(robot, sc, &plan);
+  bool filtered = (variant >= 3 || skip_nan) && n >= kFilterMinBatch;
+  const CullPlan* plan = nullptr;
+  static const AcroScene empty_scene{};
+  if (filtered) {
+    cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
     if (e != cudaSuccess) return e;
+    // the grid's cull is only good for margins well inside the filter tolerance
+    if (near_mask && !(margin <= 0.5 * (double)plan->view.delta)) filtered = false;
+  }
+  if (filtered) {
+    cudaError_t e = cudaSuccess;
     // stream-ordered scratch for the ambiguity mask (one bit per configuration)
     static std::once_flag pool_once;
     std::call_once(pool_once, [] {
@@ -351,15 +358,20 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
     if (e != cudaSuccess) return e;
     GridView view = plan->view;
     view.skip_nan = skip_nan ? 1 : 0;
-    e = launch_fk_cc_filter(robot->d32, robot->d64, view, plan->mask_bits,
-                            view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
-                            amb, st);
+    if (near_mask) {
+      view.delta = round_up_to_float((double)view.delta + margin);
+      e = cudaMemsetAsync(near_mask, 0, sizeof(uint32_t) * ((n + 31) / 32), st);
+    }
+    if (e == cudaSuccess)
+      e = launch_fk_cc_filter(robot->d32, robot->d64, view, plan->mask_bits,
+                              view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
+                              amb, near_mask, margin, st);
     cudaError_t e2 = cudaFreeAsync(amb, st);
     return e != cudaSuccess ? e : e2;
   }
-  if (variant >= 2 || (variant == 0 && !wave_supports(robot->d64)))
-    return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, nullptr,
-                                0.0, st);
+  if (near_mask || variant >= 2 || (variant == 0 && !wave_supports(robot->d64)))
+    return launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, layout, mask, near_mask,
+                                margin, st);
   static const CullTable empty_table = {};
   return launch_fk_cc_wave(robot->d64, scene ? scene->cull : empty_table, view_of<double>(scene),
                            q, n, layout, mask, st);
@@ -559,11 +571,8 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
                    void* stream) {
   if (int rc = check_batch(robot, q, mask, n)) return rc;
   if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
-  if (!near_mask)
-    return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream)),
-                  "acro_fk_cc_f64");
-  return finish(launch_fk_cc<double>(robot->d64, view_of<double>(scene), q, n, q_layout, mask,
-                                     near_mask, margin, as_stream(stream)),
+  return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream), false,
+                              near_mask, margin),
                 "acro_fk_cc_f64");
 }
 

@@ -35,11 +35,12 @@ cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, 
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
-                                uint32_t* mask, uint32_t* amb_mask, cudaStream_t st);
+                                uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
+                                double margin, cudaStream_t st);
 
 cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> sc64, const double* q,
                                int64_t n, int layout, uint32_t* mask, const uint32_t* amb_mask,
-                               cudaStream_t st);
+                               uint32_t* near_mask, double margin, cudaStream_t st);
 cudaError_t launch_filter_error(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 SceneView<float> sc32, SceneView<double> sc64, const double* q,
                                 int64_t n, double* out, cudaStream_t st);

@@ -128,12 +128,16 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
 // ---------------------------------------------------------------------------
 constexpr int kFixThreads = 256;  // one mask word (32 configurations) per thread
 
-template <int NDOF>
+// MARGIN: also report the configurations whose decisive separation is within +-margin of
+// contact (the K2' margin evaluation); the filter then ran with tolerance delta + margin, so
+// every such configuration is among the flagged ones.
+template <int NDOF, bool MARGIN>
 __global__ void __launch_bounds__(kFixThreads)
     fk_cc_fixup_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
                        const double* __restrict__ q, const int64_t n, const int layout,
                        uint32_t* __restrict__ mask, const uint32_t* __restrict__ amb_mask,
-                       const int64_t n_words) {
+                       const int64_t n_words, uint32_t* __restrict__ near_mask,
+                       const double margin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_scene = reinterpret_cast<double*>(smem_raw);
   uint16_t* s_list = reinterpret_cast<uint16_t*>(s_scene + sc.n * kSceneStride);  // [256*32]
@@ -182,10 +186,12 @@ __global__ void __launch_bounds__(kFixThreads)
 #pragma unroll
     for (int i = 0; i < NDOF; ++i)
       qv[i] = act ? (layout == ACRO_Q_AOS ? q[idx * NDOF + i] : q[(int64_t)i * n + idx]) : 0.0;
-    Verdict<double, false> v;
+    Verdict<double, MARGIN> v;
     if (__any_sync(kFull, act))
-      config_collision<double, NDOF, false>(rb, qv, s_scene, sc.n, 0.0, act, v);
+      config_collision<double, NDOF, MARGIN>(rb, qv, s_scene, sc.n, margin, act, v);
     if (act && v.hit) atomicOr(&mask[idx >> 5], 1u << (idx & 31));
+    if (MARGIN && act && v.gmin <= margin && v.gmin >= -margin)
+      atomicOr(&near_mask[idx >> 5], 1u << (idx & 31));
   }
 }
 
@@ -259,7 +265,8 @@ static int persistent_blocks(K kern, size_t smem) {
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
-                                uint32_t* mask, uint32_t* amb_mask, cudaStream_t st) {
+                                uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
+                                double margin, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kFThreads - 1) / kFThreads;
   int n_saved = 0;
@@ -293,20 +300,25 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
     if (e != cudaSuccess) return e;
   });
   if (e != cudaSuccess) return e;
-  return launch_fk_cc_fixup(rb64, sc64, q, n, layout, mask, amb_mask, st);
+  return launch_fk_cc_fixup(rb64, sc64, q, n, layout, mask, amb_mask, near_mask, margin, st);
 }
 
-// exact FP64 pass over the configurations flagged in amb_mask
+// exact FP64 pass over the configurations flagged in amb_mask (near_mask != nullptr: margin
+// mode, near_mask must be zeroed by the caller)
 cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> sc64, const double* q,
                                int64_t n, int layout, uint32_t* mask, const uint32_t* amb_mask,
-                               cudaStream_t st) {
+                               uint32_t* near_mask, double margin, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int64_t n_words = (n + 31) / 32;
   ACRO_DISPATCH_NDOF(rb64.ndof, {
     const size_t fsmem = sizeof(double) * sc64.n * kSceneStride + sizeof(uint16_t) * kFixThreads * 32;
     const int64_t fblocks = (n_words + kFixThreads - 1) / kFixThreads;
-    fk_cc_fixup_kernel<NDOF><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
-        rb64, sc64, q, n, layout, mask, amb_mask, n_words);
+    if (near_mask)
+      fk_cc_fixup_kernel<NDOF, true><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
+          rb64, sc64, q, n, layout, mask, amb_mask, n_words, near_mask, margin);
+    else
+      fk_cc_fixup_kernel<NDOF, false><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
+          rb64, sc64, q, n, layout, mask, amb_mask, n_words, nullptr, 0.0);
     count_launch();
   });
   return cudaGetLastError();

@@ -110,14 +110,25 @@ class RobotKinematics:
     def _describe_geometry(self, d, force_self):  # overridden by Robot
         pass
 
+    def _signature(self):
+        """Cheap fingerprint of everything ``_describe`` reads: the descriptor (a ~5 KB ctypes
+        struct) is only rebuilt when it changes.  Transforms are compared by value, so in-place
+        edits of ``tf_base`` / shape transforms are seen; DH tables and box sizes are assumed
+        immutable after construction (the reference never mutates them either)."""
+        tip = self.tf_tool_tip
+        return (
+            np.asarray(self.tf_base, dtype=np.float64).tobytes(),
+            None if tip is None else np.asarray(tip, dtype=np.float64).tobytes(),
+            len(self.links),
+        )
+
     def _handle(self, **kw):
-        d = self._describe(**kw)
-        key = bytes(d)
-        h = self._handles.get(key)
+        sig = (self._signature(), tuple(sorted(kw.items())))
+        h = self._handles.get(sig)
         if h is None:
-            if len(self._handles) > 8:
+            if len(self._handles) > 16:
                 self._handles.clear()
-            h = self._handles[key] = _Handle(d)
+            h = self._handles[sig] = _Handle(self._describe(**kw))
         return h.ptr
 
     def _q(self, q, dtype=torch.float64):
@@ -268,6 +279,20 @@ class Robot(RobotKinematics):
                 for s, tf in zip(self.geometry_base.s, self.geometry_base.tf_s)
             ]
         return out
+
+    def _signature(self):
+        def scene_sig(sc):
+            if sc is None:
+                return None
+            return (len(sc.s), b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in sc.tf_s))
+
+        return super()._signature() + (
+            bool(self.do_check_self_collision),
+            np.asarray(self.collision_matrix, dtype=bool).tobytes(),
+            scene_sig(self.geometry_tool),
+            scene_sig(self.geometry_base),
+            tuple(scene_sig(getattr(l, "geometry", None)) for l in self.links),
+        )
 
     def _describe_geometry(self, d, force_self):
         boxes = self._box_groups()

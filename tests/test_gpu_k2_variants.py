@@ -171,3 +171,37 @@ def test_filter_tolerance_covers_measured_fp32_error(gpu):
         print(f"delta {delta.value:.3e}  max|s32-s64| {worst_s:.3e}  max centre error {worst_p:.3e}")
         assert 0 < worst_s < delta.value / 10
         assert worst_p < delta.value / 10
+
+
+def test_margin_mode_through_the_filter(gpu):
+    """return_near=True: verdicts and the +-1e-6 m bucket from the filtered kernel (filter run
+    with tolerance delta + margin, FP64 margin evaluation of the flagged configurations) equal
+    the all-FP64 margin kernel."""
+    k = ab.Kuka()
+    rng = np.random.default_rng(5)
+    q = random_configs(1_000_000, 6, seed=41)
+    for scene in (scene16(), readme_scene()):
+        call = lambda: k.is_in_collision_batch(q, scene, return_near=True)  # noqa: E731
+        hit_s, near_s = _with_variant("simple", call)
+        hit_f, near_f = _with_variant("filter", call)
+        assert (hit_s == hit_f).all() and (near_s == near_f).all()
+    # grazing contact: a wall face within +-gap of link 1's box face
+    T = k.fk_batch(np.zeros((1, 6)), all_links=True)[0]
+    c = T[1] @ np.array([-0.3, 0, -0.05, 1.0])
+    n = 8192
+    total_near = 0
+    for gap in (1e-5, 2e-6, 5e-7, 0.0, -5e-7, -2e-6):
+        wall = ab.Scene([ab.Box(0.2, 2.0, 2.0)], [translation(c[0] + 0.4 + 0.1 + gap, c[1], c[2])])
+        qs = np.zeros((n, 6))
+        qs[:, 3:] = rng.uniform(-3, 3, (n, 3))
+        call = lambda: k.is_in_collision_batch(qs, wall, return_near=True)  # noqa: E731
+        hit_s, near_s = _with_variant("simple", call)
+        hit_f, near_f = _with_variant("filter", call)
+        assert (hit_s == hit_f).all() and (near_s == near_f).all(), gap
+        total_near += int(near_f.sum())
+    assert total_near > 0
+    # a margin wider than the filter tolerance falls back to the FP64 kernel (same answers)
+    a = k.is_in_collision_batch(q[:100_000], scene16(), return_near=True, margin=1e-3)
+    b = _with_variant("simple", lambda: k.is_in_collision_batch(q[:100_000], scene16(),
+                                                                 return_near=True, margin=1e-3))
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[1].sum() > 0
