@@ -195,6 +195,18 @@ def run_ours(args):
                        "(numpy 4x4 chain, one native box-box call per pair)"),
         }
 
+    if cpu_baseline is not None:
+        # context: the vectorised numpy oracle on one core (SURVEY 8d, item ii)
+        import numpy as _np
+
+        from oracle import np_oracle as _no
+
+        _spec, _scene = _cpu_setup()
+        _q = _np.random.default_rng(0).uniform(-_np.pi, _np.pi, (20_000, 6))
+        _t0 = time.perf_counter()
+        _no.is_in_collision(_spec, _scene, _q)
+        cpu_baseline["vectorised_numpy_1core_configs_per_s"] = len(_q) / (time.perf_counter() - _t0)
+
     import numpy as np
     import torch
     import torch.distributed as dist

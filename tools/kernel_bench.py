@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--n", type=int, default=16_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--big", action="store_true", help="add the 64 M-configuration FK point")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
     want = lambda name: not only or name in only  # noqa: E731
@@ -97,6 +98,13 @@ def main():
         n1 = 1_000_000
         f = lambda: _native.check(lib.acro_fk_f64(hk, q.data_ptr(), n1, 0, T.data_ptr(), 0, stream))  # noqa: E731
         emit("fk_f64_1M", *timed(f, args.reps), n1, 48 + 128)
+        if args.big:
+            nb = 64_000_000  # steady-state point: 11 GB of traffic per launch
+            qb = random_configs_device(nb, 6, seed=8)
+            Tb = torch.empty((nb, 4, 4), dtype=torch.float64, device="cuda")
+            f = lambda: _native.check(lib.acro_fk_f64(hk, qb.data_ptr(), nb, 0, Tb.data_ptr(), 0, stream))  # noqa: E731
+            emit("fk_f64_64M", *timed(f, args.reps), nb, 48 + 128)
+            del qb, Tb
         qs = q.t().contiguous()
         f = lambda: _native.check(lib.acro_fk_f64(hk, qs.data_ptr(), n, 1, T.data_ptr(), 0, stream))  # noqa: E731
         emit("fk_f64_soa", *timed(f, args.reps), n, 48 + 128)
