@@ -39,9 +39,9 @@ __device__ __forceinline__ double dp_edge_cost(const double* a, const double* b,
   return COST == 1 ? sqrt(acc) : acc;
 }
 
-constexpr int kDpTpw = 4;  // target nodes per warp (register blocking: sources are staged once per 32 targets)
-
-template <int COST>
+// TPW = target nodes per warp (register blocking: with 4, sources are staged once per 32
+// targets; with 1, small layers still spread over enough warps to fill the machine)
+template <int COST, int kDpTpw>
 __global__ void __launch_bounds__(kDpThreads)
     dp_layer_kernel(const double* __restrict__ q, int ndof, int64_t src0, int n_src, int64_t dst0,
                     int n_dst, const double* __restrict__ state_cost, double* __restrict__ value,
@@ -168,13 +168,20 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
     const int64_t s0 = offsets_host[l - 1], d0 = offsets_host[l];
     const int64_t ns = d0 - s0, nd = offsets_host[l + 1] - d0;
     if (ns > 0x7fffffff || nd > 0x7fffffff) return cudaErrorInvalidValue;
-    const int per_cta = (kDpThreads / 32) * kDpTpw;
+    const bool small = nd < (int64_t)sms * (kDpThreads / 32) * 4 * 2;
+    const int per_cta = (kDpThreads / 32) * (small ? 1 : 4);
     int64_t blocks = (nd + per_cta - 1) / per_cta;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;
-#define ACRO_DP_LAUNCH(C)                                                                  \
-  dp_layer_kernel<C><<<(unsigned)blocks, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0, (int)nd, \
-                                                              state_cost, value, pred, w)
+#define ACRO_DP_LAUNCH(C)                                                                         \
+  if (small)                                                                                      \
+    dp_layer_kernel<C, 1><<<(unsigned)blocks, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,     \
+                                                                   (int)nd, state_cost, value,  \
+                                                                   pred, w);                     \
+  else                                                                                            \
+    dp_layer_kernel<C, 4><<<(unsigned)blocks, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,     \
+                                                                   (int)nd, state_cost, value,  \
+                                                                   pred, w)
     switch (cost_type) {
       case 0: ACRO_DP_LAUNCH(0); break;
       case 1: ACRO_DP_LAUNCH(1); break;

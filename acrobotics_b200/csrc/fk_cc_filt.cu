@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
 // ---------------------------------------------------------------------------
 // exact pass: recompute the ambiguous configurations in FP64
 // ---------------------------------------------------------------------------
-constexpr int kFixThreads = 256;  // one mask word (32 configurations) per thread
+constexpr int kFixThreads = 256;
+constexpr int kFixWords = 4;  // mask words per thread: a CTA compacts 32768 configurations, so
+                              // that even at 0.1 % ambiguity its FP64 pass runs on a full warp
 
 // MARGIN: also report the configurations whose decisive separation is within +-margin of
 // contact (the K2' margin evaluation); the filter then ran with tolerance delta + margin, so
@@ -140,15 +142,22 @@ __global__ void __launch_bounds__(kFixThreads)
                        const double margin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_scene = reinterpret_cast<double*>(smem_raw);
-  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_scene + sc.n * kSceneStride);  // [256*32]
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_scene + sc.n * kSceneStride);  // [256*4*32]
   __shared__ int s_warp_tot[kFixThreads / 32];
   __shared__ int s_total;
   const int t = threadIdx.x;
   const unsigned lane = t & 31;
-  const int64_t w = (int64_t)blockIdx.x * kFixThreads + t;
-  unsigned bits = w < n_words ? amb_mask[w] : 0u;
+  // thread t owns words w0 + t + 256 j (coalesced reads); list order does not matter
+  const int64_t w0 = (int64_t)blockIdx.x * kFixThreads * kFixWords;
+  unsigned bits[kFixWords];
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < kFixWords; ++j) {
+    const int64_t w = w0 + t + j * kFixThreads;
+    bits[j] = w < n_words ? amb_mask[w] : 0u;
+    c += __popc(bits[j]);
+  }
   // CTA-wide exclusive scan of the bit counts
-  const int c = __popc(bits);
   int incl = c;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -170,14 +179,18 @@ __global__ void __launch_bounds__(kFixThreads)
   const int total = s_total;
   if (total == 0) return;  // CTA-uniform
   int pos = s_warp_tot[t >> 5] + incl - c;
-  while (bits) {
-    const int b = __ffs((int)bits) - 1;
-    bits &= bits - 1;
-    s_list[pos++] = (uint16_t)(t * 32 + b);
+#pragma unroll
+  for (int j = 0; j < kFixWords; ++j) {
+    unsigned bj = bits[j];
+    while (bj) {
+      const int b = __ffs((int)bj) - 1;
+      bj &= bj - 1;
+      s_list[pos++] = (uint16_t)((t + j * kFixThreads) * 32 + b);
+    }
   }
   for (int k = t; k < sc.n * kSceneStride; k += kFixThreads) s_scene[k] = sc.boxes[k];
   __syncthreads();
-  const int64_t cfg0 = (int64_t)blockIdx.x * kFixThreads * 32;
+  const int64_t cfg0 = w0 * 32;
   for (int base = 0; base < total; base += kFixThreads) {
     const int k = base + t;
     const bool act = k < total;
@@ -311,14 +324,21 @@ cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> s
   if (n <= 0) return cudaSuccess;
   const int64_t n_words = (n + 31) / 32;
   ACRO_DISPATCH_NDOF(rb64.ndof, {
-    const size_t fsmem = sizeof(double) * sc64.n * kSceneStride + sizeof(uint16_t) * kFixThreads * 32;
-    const int64_t fblocks = (n_words + kFixThreads - 1) / kFixThreads;
-    if (near_mask)
-      fk_cc_fixup_kernel<NDOF, true><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
-          rb64, sc64, q, n, layout, mask, amb_mask, n_words, near_mask, margin);
-    else
-      fk_cc_fixup_kernel<NDOF, false><<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(
-          rb64, sc64, q, n, layout, mask, amb_mask, n_words, nullptr, 0.0);
+    const size_t fsmem = sizeof(double) * sc64.n * kSceneStride +
+                         sizeof(uint16_t) * kFixThreads * kFixWords * 32;
+    const int64_t per_cta = (int64_t)kFixThreads * kFixWords;
+    const int64_t fblocks = (n_words + per_cta - 1) / per_cta;
+    if (near_mask) {
+      auto kern = fk_cc_fixup_kernel<NDOF, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      kern<<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(rb64, sc64, q, n, layout, mask, amb_mask,
+                                                          n_words, near_mask, margin);
+    } else {
+      auto kern = fk_cc_fixup_kernel<NDOF, false>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      kern<<<(unsigned)fblocks, kFixThreads, fsmem, st>>>(rb64, sc64, q, n, layout, mask, amb_mask,
+                                                          n_words, nullptr, 0.0);
+    }
     count_launch();
   });
   return cudaGetLastError();
