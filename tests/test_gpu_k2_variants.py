@@ -205,3 +205,44 @@ def test_margin_mode_through_the_filter(gpu):
     b = _with_variant("simple", lambda: k.is_in_collision_batch(q[:100_000], scene16(),
                                                                  return_near=True, margin=1e-3))
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[1].sum() > 0
+
+
+def test_full_size_properties(gpu):
+    """BASELINE config 3 at full size (100 M configurations, device resident): the filtered
+    kernel and the all-FP64 wavefront kernel return the same 12.5 MB bit mask, shards
+    concatenate to the whole, joint angles are 2*pi periodic, and the host-buffer pipeline
+    agrees with the device path."""
+    import torch
+
+    from acrobotics_b200.synthetic import random_configs_device
+
+    k = ab.Kuka()
+    scene = scene16()
+    n = 100_000_000
+    q = random_configs_device(n, 6, seed=1000)
+    words = k.is_in_collision_batch(q, scene, packed=True)
+    assert words.shape == ((n + 31) // 32,)
+    wave = _with_variant("wave", lambda: k.is_in_collision_batch(q, scene, packed=True))
+    assert torch.equal(words, wave)
+    del wave
+    rate = float(k.is_in_collision_batch(q[: 1 << 22], scene).float().mean())
+    assert 0.68 < rate < 0.74
+    # shards (cut on a multiple of 32) concatenate to the whole
+    cut = 32 * 1_234_567
+    a = k.is_in_collision_batch(q[:cut], scene, packed=True)
+    b = k.is_in_collision_batch(q[cut:], scene, packed=True)
+    assert torch.equal(torch.cat([a, b]), words)
+    del a, b
+    # periodicity on a 4 M slice: q + 2 pi rounds differently, verdicts differ only at contact
+    sl = q[: 1 << 22]
+    h0 = k.is_in_collision_batch(sl, scene)
+    h1 = k.is_in_collision_batch(sl + 2 * np.pi, scene)
+    assert float((h0 != h1).float().mean()) < 1e-5
+    # host-buffer pipeline (chunked H2D / kernel / D2H) == device path on an 8 M prefix
+    m = 8_000_000
+    lib = _native.load()
+    q_host = q[:m].cpu().pin_memory()
+    mask_host = torch.zeros((m + 31) // 32, dtype=torch.int32).pin_memory()
+    _native.check(lib.acro_fk_cc_f64_host(k._handle(), scene.native_handle(), q_host.data_ptr(), m,
+                                          mask_host.data_ptr(), 1 << 20))
+    assert torch.equal(mask_host.cuda(), words[: (m + 31) // 32])
