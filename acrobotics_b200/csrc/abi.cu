@@ -214,6 +214,25 @@ int k2_variant() {
   return v;
 }
 
+std::atomic<int> g_split{-1};  // -1 auto, 0 off, k > 0: split after slot k
+
+// Slot after which the filtered kernel hands undecided configurations to its second pass.
+// Auto: after the second link when there is a scene and the chain is long enough for the tail
+// to matter; a scene-less (self-collision only) call decides nothing early, so no split.
+int k2_split_slot(const AcroRobot* robot, const AcroScene* scene) {
+  int v = g_split.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("ACRO_K2_SPLIT");
+    if (e) {
+      v = std::atoi(e);
+      g_split.store(v < 0 ? -1 : v);
+    }
+  }
+  if (v < 0) v = (scene && scene->n > 0 && robot->d32.ndof >= 5) ? 2 : 0;
+  if (v >= robot->d32.ndof) v = 0;
+  return v;
+}
+
 int grid_dim_setting() {
   int d = g_grid_dim.load(std::memory_order_relaxed);
   if (d < 0) {
@@ -365,7 +384,7 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
     if (e == cudaSuccess)
       e = launch_fk_cc_filter(robot->d32, robot->d64, view, plan->mask_bits,
                               view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
-                              amb, near_mask, margin, st);
+                              amb, near_mask, margin, k2_split_slot(robot, scene), st);
     cudaError_t e2 = cudaFreeAsync(amb, st);
     return e != cudaSuccess ? e : e2;
   }
@@ -409,6 +428,12 @@ int acro_set_option(const char* name, const char* value) {
     const int k = parse_variant(v);
     if (k < 0) return fail(ACRO_E_INVALID, "k2_variant: filter | wave | simple");
     g_k2_variant.store(k);
+    return 0;
+  }
+  if (n == "k2_split") {
+    const int k = v == "auto" ? -1 : std::atoi(value);
+    if (k < -1 || k > ACRO_MAX_DOF) return fail(ACRO_E_INVALID, "k2_split: auto | 0 .. ndof-1");
+    g_split.store(k);
     return 0;
   }
   if (n == "k2_grid") {

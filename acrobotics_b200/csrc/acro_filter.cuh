@@ -165,11 +165,18 @@ __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
 
 // One warp, 32 configurations (one per lane; `active` false = no configuration in this lane).
 // qfn(i) returns this lane's joint value i (double).  All 32 lanes must call it together.
+// Slot window: the chain runs over slots 0 .. slot_end; boxes of slots < check_from get their
+// pose computed (and parked for later self pairs) but are not tested - a caller that already
+// decided the early slots in a previous pass resumes with check_from = first undecided slot.
+// slot_end < 0 means "to the robot's last slot".  `retired` = the lane needs no further pass
+// (surely colliding, or handed to the FP64 pass / skipped).
 // PRISM = false compiles the prismatic-joint handling out (rb.prismatic_mask must be 0).
 template <int NDOF, typename MaskT, bool PRISM, typename QFn>
 __device__ __forceinline__ void filter_chunk(const RobotDev<float>& rb, const GridView& grid,
                                              const FilterCtx& ctx, const unsigned lane,
-                                             const bool active, QFn qfn, bool& hit, bool& amb) {
+                                             const bool active, QFn qfn, bool& hit, bool& amb,
+                                             bool& retired, const int check_from = 0,
+                                             const int slot_end = -1) {
   const float* s_scene = ctx.s_scene;
   float* s_saved = ctx.s_saved;
   const float* s_half = ctx.s_half;
@@ -178,7 +185,8 @@ __device__ __forceinline__ void filter_chunk(const RobotDev<float>& rb, const Gr
   const float delta = grid.delta;
   const bool do_self = rb.check_self != 0;
   const int ndof = NDOF;
-  const int last_slot = rb.slot_begin[ndof + 2] > rb.slot_begin[ndof + 1] ? ndof + 1 : ndof;
+  const int robot_last = rb.slot_begin[ndof + 2] > rb.slot_begin[ndof + 1] ? ndof + 1 : ndof;
+  const int last_slot = (slot_end < 0 || slot_end > robot_last) ? robot_last : slot_end;
 bool done = !active;
 hit = false;
 amb = false;
@@ -232,7 +240,7 @@ amb = false;
       // ---- candidates: scene boxes from the grid, self partners from a padded cull
       MaskT ms = 0;
       unsigned mself = 0;
-      if (!done) {
+      if (!done && slot >= check_from) {
         if (n_scene > 0) {
           const float fx = (cw[0] - grid.ox) * grid.inv_cell;
           const float fy = (cw[1] - grid.oy) * grid.inv_cell;
@@ -375,7 +383,7 @@ amb = false;
       }
     }
   }
-
+  retired = done;
 }
 
 }  // namespace acro

@@ -36,7 +36,7 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
                                 uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
-                                double margin, cudaStream_t st);
+                                double margin, int split_slot, cudaStream_t st);
 
 cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> sc64, const double* q,
                                int64_t n, int layout, uint32_t* mask, const uint32_t* amb_mask,

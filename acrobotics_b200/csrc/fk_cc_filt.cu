@@ -52,27 +52,41 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Two passes per configuration (split_slot > 0).  Most decisions fall in the first links (52 %
+// of the benchmark's configurations collide at the second one), after which a warp that keeps
+// its 32 configurations together runs the remaining links with a third of its lanes.  So:
+//   pass 1  slots 0 .. split_slot for a fresh chunk; the chunk's mask words are written; the
+//           indices of the undecided configurations go to a per-warp stash;
+//   pass 2  whenever the stash holds 32 entries: those 32 configurations (from several chunks)
+//           redo the cheap FP32 chain of the early slots without tests (poses for the self
+//           pairs), run the remaining slots with full lanes, and OR late verdicts into the
+//           mask words with atomics.
+// split_slot = 0 keeps the single pass (slot windows of filter_chunk).
 template <int NDOF, typename MaskT, bool PRISM>
 __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
-                        const SceneView<float> sc, const int n_saved,
+                        const SceneView<float> sc, const int n_saved, const int split_slot,
                         const double* __restrict__ q, const int64_t n, const int layout,
                         uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [q buffers: 4 warps x 2 x 32*NDOF doubles][scene: n*16 floats]
-  // [saved poses: 4 warps x n_saved*12*32 floats][slot half extents: 16*4 floats]
-  // [item lists: 4 warps x kItemCap uint16]
+  // [q buffers: 4 warps x 3 x 32*NDOF doubles (two prefetch buffers + pass 2)]
+  // [stash: 4 warps x 64 int64][filter context]
   const int t = threadIdx.x;
   const unsigned lane = t & 31;
   const int warp = t >> 5;
-  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * 2 * 32 * NDOF;
-  unsigned char* ctx_base = smem_raw + sizeof(double) * (kFThreads / 32) * 2 * 32 * NDOF;
-  filter_ctx_stage(ctx_base, kFThreads / 32, rb, sc, n_saved);
-  const FilterCtx ctx = filter_ctx_carve(ctx_base, kFThreads / 32, warp, sc.n, n_saved);
+  constexpr int kWarps = kFThreads / 32;
+  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * 3 * 32 * NDOF;
+  long long* s_stash =
+      reinterpret_cast<long long*>(reinterpret_cast<double*>(smem_raw) + kWarps * 3 * 32 * NDOF) +
+      warp * 64;
+  unsigned char* ctx_base = smem_raw + sizeof(double) * kWarps * 3 * 32 * NDOF +
+                            sizeof(long long) * kWarps * 64;
+  filter_ctx_stage(ctx_base, kWarps, rb, sc, n_saved);
+  const FilterCtx ctx = filter_ctx_carve(ctx_base, kWarps, warp, sc.n, n_saved);
   __syncthreads();
 
   const int64_t n_chunks = (n + 31) >> 5;
-  const int64_t stride = (int64_t)gridDim.x * (kFThreads / 32);
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
 
   // asynchronous copy of one chunk's joint values into buffer `buf` (flat for AoS,
   // joint-major for SoA)
@@ -97,28 +111,75 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     cp_async_commit();
   };
 
-  int64_t chunk = (int64_t)blockIdx.x * (kFThreads / 32) + warp;
+  // One loop, one call site of filter_chunk (the kernel body must stay small enough for the
+  // instruction cache): an iteration is either pass 1 over the next chunk or pass 2 over 32
+  // stashed configurations (or over the remainder once the chunks are exhausted).
+  double* q2 = s_q + 2 * 32 * NDOF;  // pass-2 joint values, joint-major [NDOF][32]
+  int stashed = 0;                   // warp-uniform
+  int it = 0;
+  int64_t chunk = (int64_t)blockIdx.x * kWarps + warp;
   prefetch(chunk, 0);
-  for (int it = 0; chunk < n_chunks; chunk += stride, ++it) {
-    const int buf = it & 1;
-    prefetch(chunk + stride, buf ^ 1);
-    cp_async_wait<1>();
-    __syncwarp();
-    const int64_t idx = (chunk << 5) + lane;
-    // this lane's joint i sits at qp[i * qs] (row of the flat AoS copy, or column of the SoA one)
-    const double* qp = s_q + buf * 32 * NDOF + (layout == ACRO_Q_AOS ? lane * NDOF : lane);
-    const int qs = layout == ACRO_Q_AOS ? 1 : 32;
-    bool hit, amb;
-    filter_chunk<NDOF, MaskT, PRISM>(rb, grid, ctx, lane, idx < n,
-                                     [=](int i) { return qp[i * qs]; }, hit, amb);
-
-    const unsigned word = __ballot_sync(kFull, hit);
-    const unsigned aword = __ballot_sync(kFull, amb && !hit);
-    if (lane == 0) {
-      mask[chunk] = word;
-      amb_mask[chunk] = aword;
+  for (;;) {
+    const bool second = split_slot > 0 && (stashed >= 32 || (chunk >= n_chunks && stashed > 0));
+    if (!second && chunk >= n_chunks) break;
+    int64_t idx;
+    bool act;
+    const double* qp;
+    int qs, check_from, slot_end, m = 0;
+    if (second) {
+      m = stashed < 32 ? stashed : 32;
+      act = (int)lane < m;
+      idx = act ? (int64_t)s_stash[stashed - m + lane] : 0;
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i)
+          q2[i * 32 + lane] = layout == ACRO_Q_AOS ? __ldg(q + idx * NDOF + i)
+                                                   : __ldg(q + (int64_t)i * n + idx);
+      }
+      qp = q2 + lane;
+      qs = 32;
+      check_from = split_slot + 1;
+      slot_end = -1;
+    } else {
+      const int buf = it & 1;
+      prefetch(chunk + stride, buf ^ 1);
+      cp_async_wait<1>();
+      idx = (chunk << 5) + lane;
+      act = idx < n;
+      // this lane's joint i sits at qp[i * qs] (row of the flat AoS copy, column of the SoA one)
+      qp = s_q + buf * 32 * NDOF + (layout == ACRO_Q_AOS ? lane * NDOF : lane);
+      qs = layout == ACRO_Q_AOS ? 1 : 32;
+      check_from = 0;
+      slot_end = split_slot > 0 ? split_slot : -1;
     }
-    __syncwarp();  // every lane is done with buffer `buf` before it is refilled
+    __syncwarp();
+
+    bool hit, amb, retired;
+    filter_chunk<NDOF, MaskT, PRISM>(rb, grid, ctx, lane, act, [=](int i) { return qp[i * qs]; },
+                                     hit, amb, retired, check_from, slot_end);
+
+    if (second) {
+      if (act && hit) atomicOr(&mask[idx >> 5], 1u << (idx & 31));
+      if (act && amb && !hit) atomicOr(&amb_mask[idx >> 5], 1u << (idx & 31));
+      stashed -= m;
+    } else {
+      const unsigned word = __ballot_sync(kFull, hit);
+      const unsigned aword = __ballot_sync(kFull, amb && !hit);
+      if (lane == 0) {
+        mask[chunk] = word;
+        amb_mask[chunk] = aword;
+      }
+      if (split_slot > 0) {
+        // undecided and unambiguous configurations continue in pass 2
+        const bool cont = act && !retired && !amb;
+        const unsigned cm = __ballot_sync(kFull, cont);
+        if (cont) s_stash[stashed + __popc(cm & ((1u << lane) - 1u))] = (long long)idx;
+        stashed += __popc(cm);
+      }
+      chunk += stride;
+      ++it;
+    }
+    __syncwarp();  // buffers, stash entries and this chunk's mask words are settled
   }
   cp_async_wait<0>();
 }
@@ -261,7 +322,8 @@ cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, 
 // ---------------------------------------------------------------------------
 size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
   const int warps = kFThreads / 32;
-  return sizeof(double) * warps * 2 * 32 * ndof + filter_ctx_bytes(warps, n_scene, n_saved);
+  return sizeof(double) * warps * 3 * 32 * ndof + sizeof(long long) * warps * 64 +
+         filter_ctx_bytes(warps, n_scene, n_saved);
 }
 
 // resident CTAs of the persistent filter kernel on the current device
@@ -279,7 +341,7 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
                                 uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
-                                double margin, cudaStream_t st) {
+                                double margin, int split_slot, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kFThreads - 1) / kFThreads;
   int n_saved = 0;
@@ -296,8 +358,8 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
         if (e2 != cudaSuccess) return e2;
       }
       const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
-      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, q, n, layout, mask,
-                                                      amb_mask);
+      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, split_slot, q, n,
+                                                      layout, mask, amb_mask);
       return cudaSuccess;
     };
     const bool prism = rb32.prismatic_mask != 0;

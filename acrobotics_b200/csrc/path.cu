@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     if (!__any_sync(kFull, active)) break;
 
     const double s = path_param(k, n_steps, step);
-    bool hit, amb;
+    bool hit, amb, retired;
     filter_chunk<NDOF, MaskT, true>(
         rb, grid, ctx, lane, active,
         [&](int i) { return (1.0 - s) * s_ab[i * 32 + lane] + s * s_ab[(NDOF + i) * 32 + lane]; },
-        hit, amb);
+        hit, amb, retired);
     if (active) {
       if (hit) {
         atomicOr(&mask[seg >> 5], 1u << (seg & 31));

@@ -103,8 +103,10 @@ int acro_device_count(void);
 /* Tuning knobs (process wide; defaults are the production settings):
  *   "k2_variant" = "filter" (default) | "wave" | "simple": kernel behind acro_fk_cc_f64
  *                  without a near mask; all variants return identical verdicts;
+ *   "k2_split"   = "auto" (default) | 0 | k: slot after which the filtered kernel regroups the
+ *                  still undecided configurations into full warps (0 = single pass);
  *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 96).
- * The environment variables ACRO_K2_VARIANT / ACRO_K2_GRID set the initial values.    */
+ * The environment variables ACRO_K2_VARIANT / ACRO_K2_SPLIT / ACRO_K2_GRID set the initial values.    */
 int acro_set_option(const char* name, const char* value);
 
 /* Robot(links, joint_limits) + geometry  ->  immutable device descriptor.

@@ -246,3 +246,24 @@ def test_full_size_properties(gpu):
     _native.check(lib.acro_fk_cc_f64_host(k._handle(), scene.native_handle(), q_host.data_ptr(), m,
                                           mask_host.data_ptr(), 1 << 20))
     assert torch.equal(mask_host.cuda(), words[: (m + 31) // 32])
+
+
+def test_split_pass_does_not_change_verdicts(gpu):
+    """The two-pass schedule (regrouping undecided configurations after slot k) is only a
+    schedule: every split point gives the verdicts of the FP64 kernel."""
+    g = golden("cc_kuka.npz")
+    q = random_configs(700_001, 6, seed=51)
+    cases = [(ab.Kuka(), q, scene16()), (kuka_with_tool(g), q[:300_000], scene16()),
+             (ab.KukaOnRail(), random_configs(300_000, 7, seed=52), scene16()),
+             (ab.Kuka(), q[:300_000], readme_scene())]
+    try:
+        for robot, qq, scene in cases:
+            ref = _with_variant("simple", lambda: robot.is_in_collision_batch(qq, scene))
+            for split in ("auto", 0, 1, 2, 3, 5):
+                _native.set_option("k2_split", split)
+                got = robot.is_in_collision_batch(qq, scene)
+                assert (got == ref).all(), (type(robot).__name__, split, int((got != ref).sum()))
+                hit, near = robot.is_in_collision_batch(qq[:100_000], scene, return_near=True)
+                assert (hit == ref[:100_000]).all()
+    finally:
+        _native.set_option("k2_split", "auto")
