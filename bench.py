@@ -34,7 +34,7 @@ WORKLOAD = "Kuka 6-DOF fused FK+collision vs 16-box synthetic Scene (seed 0), q~
 # FK 63 flop/joint * 6 + 18 flop/link box * 6 = 486; 6*16 + 6 = 102 box pairs * 252 flop
 W_FULL_FLOP = 486 + 102 * 252
 BYTES_PER_CONFIG = 48.125  # 6 f64 in, 1 bit out
-K2_KERNEL = "acro::fk_cc_filter_kernel<6,uint32_t> (+ acro::fk_cc_fixup_kernel<6>, ~5 % of the step)"
+K2_KERNEL = "acro::fk_cc_filter_kernel<6,uint32_t> (+ acro::fk_cc_fixup_kernel<6>, ~2 % of the step)"
 
 
 def _load_k2_profile():
