@@ -2,6 +2,7 @@
 // handle management, argument validation, error reporting, the host-buffer
 // pipeline and the FMA-peak micro-benchmark.  No kernels of the hot path live
 // here; see fk.cu, fk_cc.cu, jac_ik.cu, path.cu.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -604,9 +605,28 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
 int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, void* stream) {
   if (int rc = check_batch(robot, q, mask, n)) return rc;
-  return finish(launch_fk_cc<float>(robot->d32, view_of<float>(scene), q, n, q_layout, mask,
-                                    nullptr, 0.f, as_stream(stream)),
-                "acro_fk_cc_f32");
+  cudaStream_t st = as_stream(stream);
+  if (k2_variant() < 3 || n < kFilterMinBatch || q_layout != ACRO_Q_AOS)
+    return finish(launch_fk_cc<float>(robot->d32, view_of<float>(scene), q, n, q_layout, mask,
+                                      nullptr, 0.f, st),
+                  "acro_fk_cc_f32");
+  // large batches: the joint values are widened (exactly) chunk by chunk and go through the
+  // filtered FP64-exact path - faster than the all-FP32 kernel and without its rounding
+  const int ndof = robot->d64.ndof;
+  const int64_t chunk = 1 << 24;  // multiple of 32: chunk boundaries fall on mask words
+  double* tmp = nullptr;
+  cudaError_t e = cudaMallocAsync(&tmp, sizeof(double) * std::min<int64_t>(n, chunk) * ndof, st);
+  for (int64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - done);
+    e = launch_widen(q + done * ndof, tmp, m * ndof, st);
+    if (e == cudaSuccess)
+      e = run_fk_cc_f64(robot, scene, tmp, m, ACRO_Q_AOS, mask + done / 32, st);
+  }
+  if (tmp) {
+    cudaError_t e2 = cudaFreeAsync(tmp, st);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_fk_cc_f32");
 }
 
 // ---------------------------------------------------------------------------

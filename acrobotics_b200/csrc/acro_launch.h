@@ -45,6 +45,7 @@ cudaError_t launch_filter_error(const RobotDev<float>& rb32, const RobotDev<doub
                                 SceneView<float> sc32, SceneView<double> sc64, const double* q,
                                 int64_t n, double* out, cudaStream_t st);
 
+cudaError_t launch_widen(const float* in, double* out, int64_t count, cudaStream_t st);
 cudaError_t launch_collide_boxes(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,
                                  cudaStream_t st);
 
@@ -132,12 +133,21 @@ __device__ __forceinline__ void load_q(real* qv, real* s_q, const real* __restri
 template <typename real, int W>
 __device__ __forceinline__ void load_row(real* dst, const real* __restrict__ src, bool vec) {
   constexpr int PER = 16 / sizeof(real);
+  constexpr int PER8 = 8 / sizeof(real);
   if (W % PER == 0 && vec) {
     const int4* s4 = reinterpret_cast<const int4*>(src);
 #pragma unroll
     for (int k = 0; k < W / PER; ++k) {
       const int4 v = __ldg(s4 + k);
       reinterpret_cast<int4*>(dst)[k] = v;
+    }
+  } else if (W % PER8 == 0 && vec) {
+    // rows that are only 8-byte aligned (six floats): 8-byte loads
+    const int2* s2 = reinterpret_cast<const int2*>(src);
+#pragma unroll
+    for (int k = 0; k < W / PER8; ++k) {
+      const int2 v = __ldg(s2 + k);
+      reinterpret_cast<int2*>(dst)[k] = v;
     }
   } else {
 #pragma unroll

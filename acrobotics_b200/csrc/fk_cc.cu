@@ -73,6 +73,20 @@ __global__ void __launch_bounds__(kTile)
   if ((threadIdx.x & 31) == 0 && idx < n) mask[idx >> 5] = word;
 }
 
+// widen joint values (exact): the FP32-input entry point feeds the FP64-exact K2 path
+__global__ void __launch_bounds__(256)
+    widen_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < count) out[i] = (double)in[i];
+}
+
+cudaError_t launch_widen(const float* in, double* out, int64_t count, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  widen_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(in, out, count);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_collide_boxes(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,
                                  cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -154,6 +154,9 @@ int acro_fk_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t 
 int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
                    void* stream);
+/* FP32 joint values.  Small batches run an all-FP32 kernel (poses good to ~1e-5); large AoS
+ * batches are widened exactly and take the FP64-exact filtered path, i.e. the verdicts are
+ * those of acro_fk_cc_f64 at the float-valued joint angles.                              */
 int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, void* stream);
 /* Same, HOST buffers: pipelined H2D/kernel/D2H inside the call.                 */

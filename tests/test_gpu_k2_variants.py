@@ -267,3 +267,15 @@ def test_split_pass_does_not_change_verdicts(gpu):
                 assert (hit == ref[:100_000]).all()
     finally:
         _native.set_option("k2_split", "auto")
+
+
+def test_fp32_input_takes_the_exact_path(gpu):
+    """Large FP32-input batches: verdicts of the FP64 kernel at the float-valued angles."""
+    k = ab.Kuka()
+    scene = scene16()
+    q = random_configs(300_000, 6, seed=61)
+    q32 = q.astype(np.float32)
+    got = k.is_in_collision_batch(q32, scene, dtype="f32")
+    ref = _with_variant("simple", lambda: k.is_in_collision_batch(q32.astype(np.float64), scene))
+    assert (got == ref).all()
+    assert (got != k.is_in_collision_batch(q, scene)).mean() < 1e-4  # only the rounding of q
