@@ -279,3 +279,14 @@ def test_fp32_input_takes_the_exact_path(gpu):
     ref = _with_variant("simple", lambda: k.is_in_collision_batch(q32.astype(np.float64), scene))
     assert (got == ref).all()
     assert (got != k.is_in_collision_batch(q, scene)).mean() < 1e-4  # only the rounding of q
+
+
+def test_scene_size_limits(gpu):
+    """The largest supported scene (64 boxes: one uint64 candidate word per grid cell) and the
+    error beyond it."""
+    k = ab.Kuka()
+    q = random_configs(100_000, 6, seed=71)
+    big = scene16(seed=7, n_boxes=64)
+    _all_variants_agree(k, q, big)
+    with pytest.raises(ValueError):
+        k.is_in_collision_batch(q[:10], scene16(seed=7, n_boxes=65))
