@@ -142,6 +142,9 @@ cudaError_t launch_jac(const RobotDev<double>& rb, const double* q, int64_t n, i
 struct Arm2Sol {
   double q[4][3];  // [pos_a, pos_b, neg_a, neg_b] x (q1, q2, q3)
   bool pos, neg;
+  // by-products reused by kuka_ik: sin/cos(q1_pos), cos/sin(q3) per q1 branch, and the
+  // (y, x) arguments of the q2 = atan2(y, x) of every solution
+  double s1, c1, c3[2], s3[2], y2[4], x2[4];
 };
 
 // reach test + snap of arm_2.py:37-45; returns false when unreachable
@@ -153,12 +156,22 @@ __device__ __forceinline__ bool c3_branch(double& c3, double& s3) {
   return true;
 }
 
-// inverse_kinematics/arm_2.py:5-104
+// atan2(-y, -x) from r = atan2(y, x): the reflected point lies half a turn away, on the side
+// IEEE atan2 picks from the sign of y (signed zeros included).  Agrees with a direct
+// evaluation to an ulp of pi; the closed forms below use it wherever the reference evaluates
+// both atan2(y, x) and atan2(-y, -x).
+__device__ __forceinline__ double atan2_reflected(double r, double y) {
+  return signbit(y) ? r + CUDART_PI : r - CUDART_PI;
+}
+
+// inverse_kinematics/arm_2.py:5-104.  Transcendentals are evaluated once and reused through
+// exact identities (the reference recomputes them): sin/cos(q1_neg) = -sin/cos(q1_pos),
+// atan2(-s3, c3) = -atan2(s3, c3), cos(q3b) = c3 and sin(q3a) = s3 (arm_2.py:65, :76-77).
 __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1, double a2,
                                         double a3, Arm2Sol& S) {
   const double nan = CUDART_NAN;
   const double q1_pos = atan2(y, x);
-  const double q1_neg = atan2(-y, -x);
+  const double q1_neg = atan2_reflected(q1_pos, y);
   const double den = 2 * a2 * a3;
   const double num = a1 * a1 - a2 * a2 - a3 * a3 + x * x + y * y + z * z;
   const double L = sqrt(x * x + y * y);
@@ -167,38 +180,49 @@ __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1,
 
   double s1, c1, c3, s3 = 0;
   sincos(q1_pos, &s1, &c1);
+  S.s1 = s1;
+  S.c1 = c1;
   c3 = (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
   S.pos = c3_branch(c3, s3);
+  S.c3[0] = c3;
+  S.s3[0] = s3;
   if (S.pos) {
-    const double q3a = atan2(s3, c3), q3b = atan2(-s3, c3);
-    const double cc = cos(q3b), ss = sin(q3a);  // sic: arm_2.py:65
+    const double q3a = atan2(s3, c3);
+    const double cc = c3, ss = s3;
     S.q[0][0] = q1_pos;
-    S.q[0][1] = atan2(-a3 * ss * (L - a1) + z * (a2 + a3 * cc),
-                      a3 * ss * z + (L - a1) * (a2 + a3 * cc));
+    S.y2[0] = -a3 * ss * (L - a1) + z * (a2 + a3 * cc);
+    S.x2[0] = a3 * ss * z + (L - a1) * (a2 + a3 * cc);
     S.q[0][2] = q3a;
     S.q[1][0] = q1_pos;
-    S.q[1][1] = atan2(a3 * ss * (L - a1) + z * (a2 + a3 * cc),
-                      -a3 * ss * z + (L - a1) * (a2 + a3 * cc));
-    S.q[1][2] = q3b;
+    S.y2[1] = a3 * ss * (L - a1) + z * (a2 + a3 * cc);
+    S.x2[1] = -a3 * ss * z + (L - a1) * (a2 + a3 * cc);
+    S.q[1][2] = -q3a;
+    S.q[0][1] = atan2(S.y2[0], S.x2[0]);
+    S.q[1][1] = atan2(S.y2[1], S.x2[1]);
   }
-  sincos(q1_neg, &s1, &c1);
-  c3 = (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
+  c3 = (num + 2 * a1 * s1 * y + 2 * a1 * x * c1) / den;
   S.neg = c3_branch(c3, s3);
+  S.c3[1] = c3;
+  S.s3[1] = s3;
   if (S.neg) {
-    const double q3a = atan2(s3, c3), q3b = atan2(-s3, c3);
-    const double ss = sin(q3a), cc = cos(q3b);  // arm_2.py:76-77
+    const double q3a = atan2(s3, c3);
+    const double ss = s3, cc = c3;
     S.q[2][0] = q1_neg;
-    S.q[2][1] = atan2(a3 * ss * (L + a1) + z * (a2 + a3 * cc),
-                      a3 * ss * z - (L + a1) * (a2 + a3 * cc));
+    S.y2[2] = a3 * ss * (L + a1) + z * (a2 + a3 * cc);
+    S.x2[2] = a3 * ss * z - (L + a1) * (a2 + a3 * cc);
     S.q[2][2] = q3a;
     S.q[3][0] = q1_neg;
-    S.q[3][1] = atan2(-a3 * ss * (L + a1) + z * (a2 + a3 * cc),
-                      -a3 * ss * z - (L + a1) * (a2 + a3 * cc));
-    S.q[3][2] = q3b;
+    S.y2[3] = -a3 * ss * (L + a1) + z * (a2 + a3 * cc);
+    S.x2[3] = -a3 * ss * z - (L + a1) * (a2 + a3 * cc);
+    S.q[3][2] = -q3a;
+    S.q[2][1] = atan2(S.y2[2], S.x2[2]);
+    S.q[3][1] = atan2(S.y2[3], S.x2[3]);
   }
 }
 
-// inverse_kinematics/spherical_wrist.py:5-30; Rb, R row-major 3x3
+// inverse_kinematics/spherical_wrist.py:5-30; Rb, R row-major 3x3.  The mirrored solution
+// follows from the first one: atan2(-a1, -a0) and atan2(-sz, nz) are reflections,
+// atan2(-A, a2) = -atan2(A, a2).
 __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, double* sol1,
                                          double* sol2) {
   // Rrel = Rb^T R ; a = Rrel[:,2], s_z = Rrel[2,1], n_z = Rrel[2,0]
@@ -211,9 +235,9 @@ __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, doub
   sol1[0] = atan2(a1, a0);
   sol1[1] = atan2(A, a2);
   sol1[2] = atan2(sz, -nz);
-  sol2[0] = atan2(-a1, -a0);
-  sol2[1] = atan2(-A, a2);
-  sol2[2] = atan2(-sz, nz);
+  sol2[0] = atan2_reflected(sol1[0], a1);
+  sol2[1] = -sol1[1];
+  sol2[2] = atan2_reflected(sol1[2], sz);
 }
 
 // Kuka.ik for one pose (robot_examples.py:188-218).  T: 16 doubles row-major.
@@ -276,13 +300,16 @@ __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const do
 #pragma unroll
       for (int e = 0; e < 9; ++e) F.r[e] = (e % 4 == 0) ? 1.0 : 0.0;
       F.p[0] = F.p[1] = F.p[2] = 0.0;
-      double s, c;
-      sincos(q1, &s, &c);
-      tf_mul_dh<double>(F, c, s, half_pi_cos, 1.0, a1, 0.0);
-      sincos(q2, &s, &c);
-      tf_mul_dh<double>(F, c, s, 1.0, 0.0, a2, 0.0);
-      sincos(q3, &s, &c);
-      tf_mul_dh<double>(F, c, s, half_pi_cos, 1.0, d4, 0.0);
+      // sines and cosines of the arm angles without evaluating them again: q1_neg is q1_pos
+      // plus half a turn; q2 = atan2(y2, x2); sin/cos(q3a + pi/2) = (c3, -s3) and
+      // sin/cos(-q3a + pi/2) = (c3, s3)
+      const int br = k >> 1;
+      const double sg = br ? -1.0 : 1.0;
+      tf_mul_dh<double>(F, sg * S.c1, sg * S.s1, half_pi_cos, 1.0, a1, 0.0);
+      const double h = sqrt(S.x2[k] * S.x2[k] + S.y2[k] * S.y2[k]);
+      const double inv = h > 0.0 ? 1.0 / h : 0.0;
+      tf_mul_dh<double>(F, h > 0.0 ? S.x2[k] * inv : 1.0, S.y2[k] * inv, 1.0, 0.0, a2, 0.0);
+      tf_mul_dh<double>(F, (k & 1) ? S.s3[br] : -S.s3[br], S.c3[br], half_pi_cos, 1.0, d4, 0.0);
       double w1[3], w2[3];
       wrist_ik(F.r, Tw.r, w1, w2);
       sol[2 * k][0] = q1; sol[2 * k][1] = q2; sol[2 * k][2] = q3;
