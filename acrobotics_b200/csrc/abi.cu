@@ -37,7 +37,11 @@ struct CullPlan {
   int mask_bits;
   void* cells;
   GridView view;
+  int pins;            // host threads between get_plan and the end of their launches
+  uint64_t last_use;   // for eviction (a scene keeps at most kMaxPlans plans)
 };
+
+constexpr size_t kMaxPlans = 8;
 
 struct AcroScene {
   int32_t n;
@@ -246,9 +250,24 @@ int grid_dim_setting() {
 }
 
 // Find or build the candidate grid + filter tolerance for (robot geometry, scene).
+// The returned plan is pinned: call release_plan once the kernels that use it are enqueued.
+// (Eviction frees a plan's grid with cudaFree, which waits for kernels still running.)
+void release_plan(const AcroScene* scene, const CullPlan* plan) {
+  if (!plan) return;
+  std::lock_guard<std::mutex> lock(scene->mu);
+  --const_cast<CullPlan*>(plan)->pins;
+}
+
+struct PlanPin {  // RAII holder
+  const AcroScene* scene = nullptr;
+  const CullPlan* plan = nullptr;
+  ~PlanPin() { release_plan(scene, plan); }
+};
+
 cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullPlan** out) {
   std::lock_guard<std::mutex> lock(scene->mu);
-  for (const CullPlan* p : scene->plans) {
+  static std::atomic<uint64_t> clock{0};
+  for (CullPlan* p : scene->plans) {
     if (p->n_classes != robot->n_classes || p->reach != robot->reach ||
         p->dim != grid_dim_setting())
       continue;
@@ -257,11 +276,27 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
     for (int c = 0; same && c < p->n_classes; ++c)
       same = p->class_radius[c] == robot->class_radius[c];
     if (same) {
+      ++p->pins;
+      p->last_use = ++clock;
       *out = p;
       return cudaSuccess;
     }
   }
+  // a robot whose base keeps moving through one scene would otherwise pile up grids
+  while (scene->plans.size() >= kMaxPlans) {
+    size_t victim = scene->plans.size();
+    for (size_t k = 0; k < scene->plans.size(); ++k)
+      if (scene->plans[k]->pins == 0 &&
+          (victim == scene->plans.size() || scene->plans[k]->last_use < scene->plans[victim]->last_use))
+        victim = k;
+    if (victim == scene->plans.size()) break;  // everything is in use: grow instead
+    cudaFree(scene->plans[victim]->cells);
+    delete scene->plans[victim];
+    scene->plans.erase(scene->plans.begin() + victim);
+  }
   CullPlan* p = new CullPlan();
+  p->pins = 1;
+  p->last_use = ++clock;
   p->n_classes = robot->n_classes;
   for (int c = 0; c < p->n_classes; ++c) p->class_radius[c] = robot->class_radius[c];
   for (int k = 0; k < 3; ++k) p->centre[k] = robot->centre[k];
@@ -354,9 +389,12 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
   bool filtered = (variant >= 3 || skip_nan) && n >= kFilterMinBatch;
   const CullPlan* plan = nullptr;
   static const AcroScene empty_scene{};
+  PlanPin pin;
   if (filtered) {
     cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
     if (e != cudaSuccess) return e;
+    pin.scene = scene ? scene : &empty_scene;
+    pin.plan = plan;
     // the grid's cull is only good for margins well inside the filter tolerance
     if (near_mask && !(margin <= 0.5 * (double)plan->view.delta)) filtered = false;
   }
@@ -559,7 +597,9 @@ void acro_scene_destroy(AcroScene* scene) {
 int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot) {
   if (!scene || !robot) return fail(ACRO_E_INVALID, "NULL handle");
   const CullPlan* plan = nullptr;
-  return finish(get_plan(robot, scene, &plan), "acro_scene_prepare");
+  const cudaError_t e = get_plan(robot, scene, &plan);
+  if (e == cudaSuccess) release_plan(scene, plan);
+  return finish(e, "acro_scene_prepare");
 }
 
 int acro_collide_boxes_f64(const AcroBox* a, const AcroBox* b, int64_t n, uint32_t* mask,
@@ -847,6 +887,9 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
   const CullPlan* plan = nullptr;
   cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
   if (e != cudaSuccess) return finish(e, "acro_path_cc_f64");
+  PlanPin pin;
+  pin.scene = scene ? scene : &empty_scene;
+  pin.plan = plan;
   const int64_t n_words = (n_segments + 31) / 32;
   void* scratch = nullptr;
   e = cudaMallocAsync(&scratch, ((sizeof(uint32_t) * n_words + 7) / 8) * 8 + 8, st);
@@ -868,6 +911,7 @@ int acro_filter_tolerance(const AcroRobot* robot, const AcroScene* scene, double
   cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
   if (e != cudaSuccess) return finish(e, "acro_filter_tolerance");
   *delta = (double)plan->view.delta;
+  release_plan(scene ? scene : &empty_scene, plan);
   return 0;
 }
 

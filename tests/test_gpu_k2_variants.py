@@ -290,3 +290,16 @@ def test_scene_size_limits(gpu):
     _all_variants_agree(k, q, big)
     with pytest.raises(ValueError):
         k.is_in_collision_batch(q[:10], scene16(seed=7, n_boxes=65))
+
+
+def test_moving_base_reuses_and_evicts_plans(gpu):
+    """A robot whose base moves through one scene: every base pose gets its own candidate grid,
+    a scene keeps at most eight of them (oldest unused one evicted); verdicts stay exact."""
+    k = ab.Kuka()
+    scene = scene16()
+    q = random_configs(20_000, 6, seed=81)
+    for step in range(12):
+        k.tf_base = translation(0.05 * step, -0.03 * step, 0.01 * step)
+        _all_variants_agree(k, q, scene)
+    k.tf_base = translation(0, 0, 0)
+    _all_variants_agree(k, q, scene)  # the first plan was evicted and is rebuilt
