@@ -179,6 +179,17 @@ class Scene:
             self._handle, self._handle_key = h, key
         return self._handle
 
+    def prepare(self, robot):
+        """Build now what the first large ``robot.is_in_collision_batch(q, self)`` would
+        build: the candidate grid of the filtered kernel for this (robot, scene) pair
+        (``acro_scene_prepare``).  After it, batches of 4096 configurations and more take
+        the filtered kernel."""
+        _native.check(
+            _native.load().acro_scene_prepare(self.native_handle(), robot._handle()),
+            "acro_scene_prepare",
+        )
+        return self
+
     def _release(self):
         if self._handle is not None:
             try:

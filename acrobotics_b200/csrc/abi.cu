@@ -264,7 +264,9 @@ struct PlanPin {  // RAII holder
   ~PlanPin() { release_plan(scene, plan); }
 };
 
-cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullPlan** out) {
+// create = false: only look an existing plan up (*out stays nullptr when there is none)
+cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullPlan** out,
+                     bool create = true) {
   std::lock_guard<std::mutex> lock(scene->mu);
   static std::atomic<uint64_t> clock{0};
   for (CullPlan* p : scene->plans) {
@@ -281,6 +283,10 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
       *out = p;
       return cudaSuccess;
     }
+  }
+  if (!create) {
+    *out = nullptr;
+    return cudaSuccess;
   }
   // a robot whose base keeps moving through one scene would otherwise pile up grids
   while (scene->plans.size() >= kMaxPlans) {
@@ -379,6 +385,10 @@ void build_cull_table(const double* packed, int n, CullTable& ct) {
 }
 
 constexpr int64_t kFilterMinBatch = 4096;  // below this the plain FP64 kernel is used
+// building a candidate grid (~1 ms) only pays for batches of this size; smaller ones take the
+// filtered path when the (robot, scene) pair already has a plan (acro_scene_prepare, or an
+// earlier large batch)
+constexpr int64_t kPlanMinBatch = 1 << 16;
 
 // near_mask != nullptr: margin mode (verdicts + the configurations within +-margin of contact)
 cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
@@ -391,12 +401,13 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
   static const AcroScene empty_scene{};
   PlanPin pin;
   if (filtered) {
-    cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
+    cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan, n >= kPlanMinBatch);
     if (e != cudaSuccess) return e;
+    if (!plan) filtered = false;
     pin.scene = scene ? scene : &empty_scene;
     pin.plan = plan;
     // the grid's cull is only good for margins well inside the filter tolerance
-    if (near_mask && !(margin <= 0.5 * (double)plan->view.delta)) filtered = false;
+    if (plan && near_mask && !(margin <= 0.5 * (double)plan->view.delta)) filtered = false;
   }
   if (filtered) {
     cudaError_t e = cudaSuccess;

@@ -117,11 +117,13 @@ void acro_robot_destroy(AcroRobot* robot);
 /* Scene(shapes, tf_shapes) (geometry.py:12-14), boxes only.  n may be 0.         */
 int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out);
 void acro_scene_destroy(AcroScene* scene);
-/* Optional: build now what acro_fk_cc_f64 would otherwise build on its first call with
- * this (robot, scene) pair - the candidate grid of the filtered kernel (a few MB of
- * device memory owned by the scene handle, one synchronisation).  After it, the hot call
+/* Optional: build now what acro_fk_cc_f64 would otherwise build on its first LARGE call
+ * (>= 65536 configurations) with this (robot, scene) pair - the candidate grid of the
+ * filtered kernel (about 20 MB of device memory owned by the scene handle, ~1 ms, one
+ * synchronisation; a scene keeps the eight most recently used grids).  With a grid in
+ * place, batches of 4096 configurations and more take the filtered kernel and the hot call
  * allocates nothing but stream-ordered scratch (cudaMallocAsync) for one bit per
- * configuration.                                                                   */
+ * configuration; without one, smaller batches run the all-FP64 kernel.               */
 int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot);
 
 /* ---- the fcl.collide seam -------------------------------------------------------

@@ -25,6 +25,8 @@ def _with_variant(name, fn):
 
 
 def _all_variants_agree(robot, q, scene, self_only=False):
+    if scene is not None and not self_only:
+        scene.prepare(robot)  # batches below 64 K only take the filtered kernel with a plan
     call = (lambda: robot.is_in_self_collision_batch(q)) if self_only else (
         lambda: robot.is_in_collision_batch(q, scene))
     ref = _with_variant("simple", call)
@@ -192,6 +194,7 @@ def test_margin_mode_through_the_filter(gpu):
     total_near = 0
     for gap in (1e-5, 2e-6, 5e-7, 0.0, -5e-7, -2e-6):
         wall = ab.Scene([ab.Box(0.2, 2.0, 2.0)], [translation(c[0] + 0.4 + 0.1 + gap, c[1], c[2])])
+        wall.prepare(k)
         qs = np.zeros((n, 6))
         qs[:, 3:] = rng.uniform(-3, 3, (n, 3))
         call = lambda: k.is_in_collision_batch(qs, wall, return_near=True)  # noqa: E731
@@ -303,3 +306,20 @@ def test_moving_base_reuses_and_evicts_plans(gpu):
         _all_variants_agree(k, q, scene)
     k.tf_base = translation(0, 0, 0)
     _all_variants_agree(k, q, scene)  # the first plan was evicted and is rebuilt
+
+
+def test_small_batches_without_a_plan_use_the_fp64_kernel(gpu):
+    """No candidate grid is built for a batch below 64 K configurations (it would cost more
+    than the batch); with a prepared plan the same batch takes the filtered kernel.  Same
+    verdicts either way, and the launch counter tells which kernel ran."""
+    k = ab.Kuka()
+    q = random_configs(10_000, 6, seed=91)
+    scene = scene16(seed=11)
+    before = _native.launch_count()
+    a = k.is_in_collision_batch(q, scene)
+    assert _native.launch_count() - before == 1  # fk_cc_kernel<double>
+    scene.prepare(k)
+    before = _native.launch_count()
+    b = k.is_in_collision_batch(q, scene)
+    assert _native.launch_count() - before == 2  # filter + exact pass
+    assert (a == b).all()
