@@ -323,3 +323,74 @@ def test_small_batches_without_a_plan_use_the_fp64_kernel(gpu):
     b = k.is_in_collision_batch(q, scene)
     assert _native.launch_count() - before == 2  # filter + exact pass
     assert (a == b).all()
+
+
+def _random_rotation(rng):
+    quat = rng.normal(size=4)
+    w, x, y, z = quat / np.linalg.norm(quat)
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _random_robot(rng):
+    """A random serial chain: 3-8 joints (revolute / prismatic), 0-3 boxes per link with
+    arbitrary offsets, maybe tool and base geometry, a moved base, a random collision matrix."""
+    ndof = int(rng.integers(3, 9))
+    links = []
+    for i in range(ndof):
+        dh = ab.DHLink(float(rng.uniform(0, 0.5)), float(rng.choice([0, np.pi / 2, -np.pi / 2, 0.3])),
+                       float(rng.uniform(0, 0.4)), float(rng.uniform(-1, 1)))
+        jt = ab.JointType.prismatic if rng.random() < 0.2 else ab.JointType.revolute
+        shapes, tfs = [], []
+        for _ in range(int(rng.integers(0, 4)) if i else 1):
+            tf = np.eye(4)
+            if rng.random() < 0.5:
+                tf[:3, :3] = _random_rotation(rng)
+            tf[:3, 3] = rng.uniform(-0.2, 0.2, 3)
+            shapes.append(ab.Box(*rng.uniform(0.05, 0.4, 3)))
+            tfs.append(tf)
+        links.append(ab.Link(dh, jt, ab.Scene(shapes, tfs)))
+    robot = ab.Robot(links)
+    if rng.random() < 0.5:
+        tf = np.eye(4)
+        tf[:3, :3] = _random_rotation(rng)
+        tf[:3, 3] = rng.uniform(-0.1, 0.1, 3)
+        tip = np.eye(4)
+        tip[:3, 3] = [0, 0, 0.1]
+        robot.tool = ab.Tool([ab.Box(0.1, 0.05, 0.2), ab.Box(0.05, 0.05, 0.05)],
+                             [tf, np.eye(4)], tip)
+    if rng.random() < 0.5:
+        robot.geometry_base = ab.Scene([ab.Box(0.4, 0.4, 0.2)], [translation(0, 0, -0.1)])
+    if rng.random() < 0.5:
+        base = np.eye(4)
+        base[:3, :3] = _random_rotation(rng)
+        base[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+        robot.tf_base = base
+    cm = rng.random((ndof, ndof)) < 0.4
+    robot.collision_matrix = np.triu(cm, 2) | np.triu(cm, 2).T
+    robot.do_check_self_collision = bool(rng.random() < 0.8)
+    return robot
+
+
+def test_random_robots_and_scenes(gpu):
+    """Fuzz: the filtered kernel (candidate grid, two passes, FP32 filter, FP64 pass) against
+    the plain FP64 kernel on random chains, geometries and scenes - exact agreement - and the
+    plain kernel against the oracle on a prefix."""
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        robot = _random_robot(rng)
+        scene = scene16(seed=100 + trial, n_boxes=int(rng.integers(1, 50)))
+        q = rng.uniform(-np.pi, np.pi, (150_000, robot.ndof))
+        ref = _all_variants_agree(robot, q, scene)
+        got_self = _with_variant("filter", lambda: robot.is_in_self_collision_batch(q))
+        ref_self = _with_variant("simple", lambda: robot.is_in_self_collision_batch(q))
+        assert (got_self == ref_self).all(), trial
+        g = no.collision_margins(spec(robot), scene, q[:3000])
+        robust = np.abs(g) > 1e-6
+        assert (ref[:3000][robust] == ~(g[robust] > 0)).all(), trial
+        # the path sweep on the same robot
+        qg = q[:20_000] + rng.uniform(-0.3, 0.3, (20_000, robot.ndof))
+        call = lambda: robot.is_path_in_collision_discrete_batch(q[:20_000], qg, scene, 0.1)  # noqa: E731
+        assert (_with_variant("simple", call) == _with_variant("filter", call)).all(), trial
