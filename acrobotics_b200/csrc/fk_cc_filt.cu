@@ -14,7 +14,7 @@
 //    its pairs surely collides or all of them are surely separated; otherwise its
 //    bit is set in `amb_mask` and fk_cc_fixup_kernel recomputes exactly that
 //    configuration in FP64 (config_collision<double>, the K2' code) and patches
-//    the verdict.  For random inputs ~0.5 % of the configurations take that path.
+//    the verdict.  For random inputs ~0.1 % of the configurations take that path.
 //  * Scene candidates of a robot box come from one lookup in a precomputed grid
 //    (GridView) instead of a loop over the scene; a pair the grid drops is one
 //    that FCL's own face-axis test separates.
@@ -22,6 +22,8 @@
 //    tests of a warp's candidate pairs are redistributed over its lanes (items in
 //    a small shared-memory list, poses fetched with warp shuffles), so the
 //    15-axis test runs with dense warps although candidates are unevenly spread.
+//  * Two passes: the slots up to `split_slot` for a fresh chunk, the rest for 32 still
+//    undecided configurations regrouped from several chunks (see the kernel).
 #include <algorithm>
 #include <cstdlib>
 #include <string>
