@@ -165,9 +165,9 @@ __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
 
 // One warp, 32 configurations (one per lane; `active` false = no configuration in this lane).
 // qfn(i) returns this lane's joint value i (double).  All 32 lanes must call it together.
-// Slot window: the chain runs over slots 0 .. slot_end; boxes of slots < check_from get their
-// pose computed (and parked for later self pairs) but are not tested - a caller that already
-// decided the early slots in a previous pass resumes with check_from = first undecided slot.
+// Slot window: the chain runs over slots 0 .. slot_end; boxes of slots whose bit is clear in
+// check_mask get their pose computed (and parked for later self pairs) but are not tested - a
+// caller that splits the work into passes gives every slot to exactly one of them.
 // slot_end < 0 means "to the robot's last slot".  `retired` = the lane needs no further pass
 // (surely colliding, or handed to the FP64 pass / skipped).
 // PRISM = false compiles the prismatic-joint handling out (rb.prismatic_mask must be 0).
@@ -175,7 +175,7 @@ template <int NDOF, typename MaskT, bool PRISM, typename QFn>
 __device__ __forceinline__ void filter_chunk(const RobotDev<float>& rb, const GridView& grid,
                                              const FilterCtx& ctx, const unsigned lane,
                                              const bool active, QFn qfn, bool& hit, bool& amb,
-                                             bool& retired, const int check_from = 0,
+                                             bool& retired, const unsigned check_mask = ~0u,
                                              const int slot_end = -1) {
   const float* s_scene = ctx.s_scene;
   float* s_saved = ctx.s_saved;
@@ -240,7 +240,7 @@ amb = false;
       // ---- candidates: scene boxes from the grid, self partners from a padded cull
       MaskT ms = 0;
       unsigned mself = 0;
-      if (!done && slot >= check_from) {
+      if (!done && ((check_mask >> slot) & 1u)) {
         if (n_scene > 0) {
           const float fx = (cw[0] - grid.ox) * grid.inv_cell;
           const float fy = (cw[1] - grid.oy) * grid.inv_cell;

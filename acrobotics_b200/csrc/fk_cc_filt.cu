@@ -57,18 +57,20 @@ __device__ __forceinline__ void cp_async_wait() {
 // Two passes per configuration (split_slot > 0).  Most decisions fall in the first links (52 %
 // of the benchmark's configurations collide at the second one), after which a warp that keeps
 // its 32 configurations together runs the remaining links with a third of its lanes.  So:
-//   pass 1  slots 0 .. split_slot for a fresh chunk; the chunk's mask words are written; the
-//           indices of the undecided configurations go to a per-warp stash;
+//   pass 1  the chain up to slot split_slot for a fresh chunk, testing the slots of early_mask;
+//           the chunk's mask words are written; the indices of the undecided configurations
+//           go to a per-warp stash;
 //   pass 2  whenever the stash holds 32 entries: those 32 configurations (from several chunks)
-//           redo the cheap FP32 chain of the early slots without tests (poses for the self
-//           pairs), run the remaining slots with full lanes, and OR late verdicts into the
-//           mask words with atomics.
+//           redo the cheap FP32 chain from the start, test every slot pass 1 did not (early
+//           slots outside early_mask - by default the base and the first link, which hardly
+//           ever decide a configuration - and everything after split_slot) with full lanes,
+//           and OR late verdicts into the mask words with atomics.
 // split_slot = 0 keeps the single pass (slot windows of filter_chunk).
 template <int NDOF, typename MaskT, bool PRISM>
 __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved, const int split_slot,
-                        const double* __restrict__ q, const int64_t n, const int layout,
+                        const unsigned early_mask, const double* __restrict__ q, const int64_t n, const int layout,
                         uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [q buffers: 4 warps x 3 x 32*NDOF doubles (two prefetch buffers + pass 2)]
@@ -130,7 +132,8 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     int64_t idx;
     bool act;
     const double* qp;
-    int qs, check_from, slot_end, m = 0;
+    int qs, slot_end, m = 0;
+    unsigned check_mask;
     if (second) {
       m = stashed < 32 ? stashed : 32;
       act = (int)lane < m;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
       }
       qp = q2 + lane;
       qs = 32;
-      check_from = split_slot + 1;
+      check_mask = ~early_mask;
       slot_end = -1;
     } else {
       const int buf = it & 1;
@@ -154,14 +157,14 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
       // this lane's joint i sits at qp[i * qs] (row of the flat AoS copy, column of the SoA one)
       qp = s_q + buf * 32 * NDOF + (layout == ACRO_Q_AOS ? lane * NDOF : lane);
       qs = layout == ACRO_Q_AOS ? 1 : 32;
-      check_from = 0;
+      check_mask = split_slot > 0 ? early_mask : ~0u;
       slot_end = split_slot > 0 ? split_slot : -1;
     }
     __syncwarp();
 
     bool hit, amb, retired;
     filter_chunk<NDOF, MaskT, PRISM>(rb, grid, ctx, lane, act, [=](int i) { return qp[i * qs]; },
-                                     hit, amb, retired, check_from, slot_end);
+                                     hit, amb, retired, check_mask, slot_end);
 
     if (second) {
       if (act && hit) atomicOr(&mask[idx >> 5], 1u << (idx & 31));
@@ -354,6 +357,10 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
     if (rb32.boxes[b].save_slot + 1 > n_saved) n_saved = rb32.boxes[b].save_slot + 1;
   if (!rb32.check_self) n_saved = 0;
   cudaError_t e = cudaSuccess;
+  // pass 1 tests slots 2 .. split_slot; the base (slot 0) and the first link (slot 1) wait for
+  // pass 2 unless the split is so early that nothing else is left for pass 1
+  unsigned early_mask = split_slot > 0 ? ((2u << split_slot) - 1u) : ~0u;
+  if (split_slot >= 2) early_mask &= ~3u;
   ACRO_DISPATCH_NDOF(rb32.ndof, {
     const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved);
     auto launch = [&](auto kern) -> cudaError_t {
@@ -363,8 +370,8 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
         if (e2 != cudaSuccess) return e2;
       }
       const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
-      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, split_slot, q, n,
-                                                      layout, mask, amb_mask);
+      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, split_slot,
+                                                      early_mask, q, n, layout, mask, amb_mask);
       return cudaSuccess;
     };
     const bool prism = rb32.prismatic_mask != 0;
