@@ -106,6 +106,63 @@ __global__ void __launch_bounds__(kDpThreads)
   }
 }
 
+// Small layers (the common case: a few hundred to a few thousand nodes): one CTA per target
+// node, one or a few source nodes per thread - the whole transition is one load round trip, a
+// handful of FP64 operations and a CTA-wide arg-min, so a layer costs little more than its
+// launch.  Lowest index wins ties, like the tiled kernel.
+template <int COST>
+__global__ void __launch_bounds__(kDpThreads)
+    dp_layer_cta_kernel(const double* __restrict__ q, int ndof, int64_t src0, int n_src,
+                        int64_t dst0, const double* __restrict__ state_cost,
+                        double* __restrict__ value, int32_t* __restrict__ pred,
+                        const DpWeights w) {
+  __shared__ double s_best[kDpThreads / 32];
+  __shared__ int s_idx[kDpThreads / 32];
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double tq[kDpMaxDof];
+#pragma unroll
+  for (int i = 0; i < kDpMaxDof; ++i) tq[i] = i < ndof ? __ldg(q + (dst0 + k) * ndof + i) : 0.0;
+  double best = 1.0 / 0.0;
+  int best_j = -1;
+  for (int j = threadIdx.x; j < n_src; j += kDpThreads) {
+    double a[kDpMaxDof];
+#pragma unroll
+    for (int i = 0; i < kDpMaxDof; ++i) a[i] = i < ndof ? __ldg(q + (src0 + j) * ndof + i) : 0.0;
+    const double c = value[src0 + j] + dp_edge_cost<COST>(a, tq, w, ndof);
+    if (c < best) {
+      best = c;
+      best_j = j;
+    }
+  }
+  auto better = [](double ob, int oj, double b, int bj) {
+    return ob < b || (ob == b && oj >= 0 && (bj < 0 || oj < bj));
+  };
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+    if (better(ob, oj, best, best_j)) {
+      best = ob;
+      best_j = oj;
+    }
+  }
+  if (lane == 0) {
+    s_best[warp] = best;
+    s_idx[warp] = best_j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int v = 1; v < kDpThreads / 32; ++v)
+      if (better(s_best[v], s_idx[v], best, best_j)) {
+        best = s_best[v];
+        best_j = s_idx[v];
+      }
+    value[dst0 + k] = best + (state_cost ? state_cost[dst0 + k] : 0.0);
+    pred[dst0 + k] = best_j;
+  }
+}
+
 __global__ void dp_init_kernel(const double* __restrict__ state_cost, int64_t n0,
                                double* __restrict__ value, int32_t* __restrict__ pred) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,7 +231,10 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;
 #define ACRO_DP_LAUNCH(C)                                                                         \
-  if (small)                                                                                      \
+  if (ns <= 8192 && nd <= 65535)                                                                  \
+    dp_layer_cta_kernel<C><<<(unsigned)nd, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,        \
+                                                                state_cost, value, pred, w);     \
+  else if (small)                                                                                 \
     dp_layer_kernel<C, 1><<<(unsigned)blocks, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,     \
                                                                    (int)nd, state_cost, value,  \
                                                                    pred, w);                     \
