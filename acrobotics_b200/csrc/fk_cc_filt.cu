@@ -73,20 +73,20 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
                         const unsigned early_mask, const double* __restrict__ q, const int64_t n, const int layout,
                         uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [q buffers: 4 warps x 3 x 32*NDOF doubles (two prefetch buffers + pass 2)]
+  // [q buffers: 4 warps x 2 x 32*NDOF doubles (prefetch double buffer; pass 2 borrows the idle one)]
   // [stash: 4 warps x 64 int64][filter context]
-  // Kuka x 16 boxes: 40 KB per CTA - five CTAs per SM just fit the 227 KB.  (Keeping the joint
-  // rows of the stashed configurations in shared memory instead of re-reading them from L2 in
-  // pass 2 costs 6 KB more, drops residency to four CTAs and was measured 9 % slower.)
+  // Kuka x 16 boxes: 34 KB per CTA.  (Keeping the joint rows of the stashed configurations in
+  // shared memory instead of re-reading them from L2 in pass 2 drops residency by one CTA per
+  // SM and was measured 9 % slower.)
   const int t = threadIdx.x;
   const unsigned lane = t & 31;
   const int warp = t >> 5;
   constexpr int kWarps = kFThreads / 32;
-  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * 3 * 32 * NDOF;
+  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * 2 * 32 * NDOF;
   long long* s_stash =
-      reinterpret_cast<long long*>(reinterpret_cast<double*>(smem_raw) + kWarps * 3 * 32 * NDOF) +
+      reinterpret_cast<long long*>(reinterpret_cast<double*>(smem_raw) + kWarps * 2 * 32 * NDOF) +
       warp * 64;
-  unsigned char* ctx_base = smem_raw + sizeof(double) * kWarps * 3 * 32 * NDOF +
+  unsigned char* ctx_base = smem_raw + sizeof(double) * kWarps * 2 * 32 * NDOF +
                             sizeof(long long) * kWarps * 64;
   filter_ctx_stage(ctx_base, kWarps, rb, sc, n_saved);
   const FilterCtx ctx = filter_ctx_carve(ctx_base, kWarps, warp, sc.n, n_saved);
@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   // One loop, one call site of filter_chunk (the kernel body must stay small enough for the
   // instruction cache): an iteration is either pass 1 over the next chunk or pass 2 over 32
   // stashed configurations (or over the remainder once the chunks are exhausted).
-  double* q2 = s_q + 2 * 32 * NDOF;  // pass-2 joint values, joint-major [NDOF][32]
+  // pass 2 keeps its joint values (joint-major [NDOF][32]) in the prefetch buffer of the chunk
+  // pass 1 has just finished with: that buffer is only refilled by the next pass-1 iteration
   int stashed = 0;                   // warp-uniform
   int it = 0;
   int64_t chunk = (int64_t)blockIdx.x * kWarps + warp;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
       m = stashed < 32 ? stashed : 32;
       act = (int)lane < m;
       idx = act ? (int64_t)s_stash[stashed - m + lane] : 0;
+      double* q2 = s_q + ((it + 1) & 1) * 32 * NDOF;
       if (act) {
 #pragma unroll
         for (int i = 0; i < NDOF; ++i)
@@ -330,7 +332,7 @@ cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, 
 // ---------------------------------------------------------------------------
 size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
   const int warps = kFThreads / 32;
-  return sizeof(double) * warps * 3 * 32 * ndof + sizeof(long long) * warps * 64 +
+  return sizeof(double) * warps * 2 * 32 * ndof + sizeof(long long) * warps * 64 +
          filter_ctx_bytes(warps, n_scene, n_saved);
 }
 
