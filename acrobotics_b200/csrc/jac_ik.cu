@@ -14,6 +14,13 @@
 #include "acro_collide.cuh"
 #include "acro_launch.h"
 
+#ifndef ACRO_JAC_POS_CTAS
+#define ACRO_JAC_POS_CTAS 5
+#endif
+#ifndef ACRO_JAC_RPY_CTAS
+#define ACRO_JAC_RPY_CTAS 4
+#endif
+
 namespace acro {
 
 // flat coalesced copy of `W` reals per configuration from padded smem rows
@@ -45,7 +52,7 @@ __device__ __forceinline__ void fetch_rows(double* s_rows, const double* __restr
 // Jacobians
 // ---------------------------------------------------------------------------
 template <int NDOF, bool RPY>
-__global__ void __launch_bounds__(kTile, RPY ? 4 : 5)
+__global__ void __launch_bounds__(kTile, RPY ? ACRO_JAC_RPY_CTAS : ACRO_JAC_POS_CTAS)
     jac_kernel(const __grid_constant__ RobotDev<double> rb, const double* __restrict__ q,
                int64_t n, int layout, double* __restrict__ J, bool vec_in, bool vec_out) {
   constexpr int ROWS = RPY ? 6 : 3;
