@@ -37,6 +37,7 @@ struct CullPlan {
   int mask_bits;
   void* cells;
   GridView view;
+  int device;          // the grid lives in this device's memory
   int pins;            // host threads between get_plan and the end of their launches
   uint64_t last_use;   // for eviction (a scene keeps at most kMaxPlans plans)
 };
@@ -192,6 +193,16 @@ int check_batch(const void* robot, const void* in, const void* out, int64_t n) {
   return 0;
 }
 
+// a scene's boxes live in the memory of the device that was current at acro_scene_create
+int check_scene_device(const AcroScene* scene) {
+  if (!scene) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(ACRO_E_NOGPU, "no usable CUDA device");
+  if (dev != scene->device)
+    return fail(ACRO_E_INVALID, "scene handle was created on another CUDA device");
+  return 0;
+}
+
 int finish(cudaError_t e, const char* where) { return e == cudaSuccess ? 0 : cuda_fail(e, where); }
 
 float round_up_to_float(double x);
@@ -269,7 +280,11 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
                      bool create = true) {
   std::lock_guard<std::mutex> lock(scene->mu);
   static std::atomic<uint64_t> clock{0};
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
   for (CullPlan* p : scene->plans) {
+    if (p->device != dev) continue;
     if (p->n_classes != robot->n_classes || p->reach != robot->reach ||
         p->dim != grid_dim_setting())
       continue;
@@ -302,6 +317,7 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   }
   CullPlan* p = new CullPlan();
   p->pins = 1;
+  p->device = dev;
   p->last_use = ++clock;
   p->n_classes = robot->n_classes;
   for (int c = 0; c < p->n_classes; ++c) p->class_radius[c] = robot->class_radius[c];
@@ -647,6 +663,7 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
                    int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
                    void* stream) {
   if (int rc = check_batch(robot, q, mask, n)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
   if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
   return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream), false,
                               near_mask, margin),
@@ -656,6 +673,7 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
 int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, void* stream) {
   if (int rc = check_batch(robot, q, mask, n)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
   cudaStream_t st = as_stream(stream);
   if (k2_variant() < 3 || n < kFilterMinBatch || q_layout != ACRO_Q_AOS)
     return finish(launch_fk_cc<float>(robot->d32, view_of<float>(scene), q, n, q_layout, mask,
@@ -711,6 +729,7 @@ HostPipe g_pipe;
 int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
                         int64_t n, uint32_t* mask_host, int64_t chunk) {
   if (int rc = check_batch(robot, q_host, mask_host, n)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
   if (n == 0) return 0;
   if (chunk <= 0) chunk = 1 << 22;
   chunk = (chunk + 31) / 32 * 32;  // chunk boundaries fall on mask words
@@ -793,6 +812,7 @@ int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const do
                         double* q_out, uint8_t* valid, uint8_t* free_mask, void* stream) {
   if (int rc = check_kuka(robot)) return rc;
   if (int rc = check_batch(robot, T, q_out, n)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
   if (n > 0 && (!valid || !free_mask)) return fail(ACRO_E_INVALID, "valid/free_mask is NULL");
   cudaStream_t st = as_stream(stream);
   if (8 * n < kFilterMinBatch)
@@ -887,6 +907,7 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
                      const double* q_goal, int64_t n_segments, double max_q_step, uint32_t* mask,
                      void* stream) {
   if (int rc = check_batch(robot, q_start, mask, n_segments)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
   if (n_segments > 0 && !q_goal) return fail(ACRO_E_INVALID, "q_goal is NULL");
   if (!(max_q_step > 0.0)) return fail(ACRO_E_INVALID, "max_q_step must be > 0");
   cudaStream_t st = as_stream(stream);
