@@ -110,14 +110,16 @@ __global__ void __launch_bounds__(kDpThreads)
 // node, one or a few source nodes per thread - the whole transition is one load round trip, a
 // handful of FP64 operations and a CTA-wide arg-min, so a layer costs little more than its
 // launch.  Lowest index wins ties, like the tiled kernel.
+constexpr int kDpCtaThreads = 128;  // 8 CTAs per SM: ~1200 target nodes per wave
+
 template <int COST>
-__global__ void __launch_bounds__(kDpThreads)
+__global__ void __launch_bounds__(kDpCtaThreads, 8)
     dp_layer_cta_kernel(const double* __restrict__ q, int ndof, int64_t src0, int n_src,
                         int64_t dst0, const double* __restrict__ state_cost,
                         double* __restrict__ value, int32_t* __restrict__ pred,
                         const DpWeights w) {
-  __shared__ double s_best[kDpThreads / 32];
-  __shared__ int s_idx[kDpThreads / 32];
+  __shared__ double s_best[kDpCtaThreads / 32];
+  __shared__ int s_idx[kDpCtaThreads / 32];
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double tq[kDpMaxDof];
@@ -125,14 +127,25 @@ __global__ void __launch_bounds__(kDpThreads)
   for (int i = 0; i < kDpMaxDof; ++i) tq[i] = i < ndof ? __ldg(q + (dst0 + k) * ndof + i) : 0.0;
   double best = 1.0 / 0.0;
   int best_j = -1;
-  for (int j = threadIdx.x; j < n_src; j += kDpThreads) {
-    double a[kDpMaxDof];
+  // two source nodes per thread in flight
+  for (int j0 = threadIdx.x; j0 < n_src; j0 += 2 * kDpCtaThreads) {
+    double a[2][kDpMaxDof], v[2];
 #pragma unroll
-    for (int i = 0; i < kDpMaxDof; ++i) a[i] = i < ndof ? __ldg(q + (src0 + j) * ndof + i) : 0.0;
-    const double c = value[src0 + j] + dp_edge_cost<COST>(a, tq, w, ndof);
-    if (c < best) {
-      best = c;
-      best_j = j;
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * kDpCtaThreads;
+      const bool ok = j < n_src;
+#pragma unroll
+      for (int i = 0; i < kDpMaxDof; ++i)
+        a[u][i] = (ok && i < ndof) ? __ldg(q + (src0 + j) * ndof + i) : 0.0;
+      v[u] = ok ? value[src0 + j] : 1.0 / 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const double c = v[u] + dp_edge_cost<COST>(a[u], tq, w, ndof);
+      if (c < best) {  // ascending index within a thread: the lowest index wins ties
+        best = c;
+        best_j = j0 + u * kDpCtaThreads;
+      }
     }
   }
   auto better = [](double ob, int oj, double b, int bj) {
@@ -153,10 +166,10 @@ __global__ void __launch_bounds__(kDpThreads)
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int v = 1; v < kDpThreads / 32; ++v)
-      if (better(s_best[v], s_idx[v], best, best_j)) {
-        best = s_best[v];
-        best_j = s_idx[v];
+    for (int v2 = 1; v2 < kDpCtaThreads / 32; ++v2)
+      if (better(s_best[v2], s_idx[v2], best, best_j)) {
+        best = s_best[v2];
+        best_j = s_idx[v2];
       }
     value[dst0 + k] = best + (state_cost ? state_cost[dst0 + k] : 0.0);
     pred[dst0 + k] = best_j;
@@ -232,7 +245,7 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
     if (blocks < 1) blocks = 1;
 #define ACRO_DP_LAUNCH(C)                                                                         \
   if (ns <= 8192 && nd <= 65535)                                                                  \
-    dp_layer_cta_kernel<C><<<(unsigned)nd, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,        \
+    dp_layer_cta_kernel<C><<<(unsigned)nd, kDpCtaThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,        \
                                                                 state_cost, value, pred, w);     \
   else if (small)                                                                                 \
     dp_layer_kernel<C, 1><<<(unsigned)blocks, kDpThreads, 0, st>>>(q, ndof, s0, (int)ns, d0,     \

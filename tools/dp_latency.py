@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from acrobotics_b200 import _native
 lib = _native.load()
-L, n = 10000, 842
+L, n = 10000, int(os.environ.get("DP_N", "842"))
 rng = np.random.default_rng(0)
 q = torch.from_numpy(rng.uniform(-3, 3, (L * n, 6))).cuda()
 off = (np.arange(L + 1) * n).astype(np.int64)
