@@ -79,3 +79,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/acro_b200.h compiles as C99 and examples/c_abi_smoke.c (no Python, no torch)
+    builds against the library; it is run on the GPU box by tests/test_gpu_parity.py."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = os.path.join(ROOT, "include", "acro_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header], check=True)
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    _native.load()
+    exe = tmp_path / "c_abi_smoke"
+    subprocess.run(
+        [gcc, "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", f"{cuda}/include",
+         os.path.join(ROOT, "examples", "c_abi_smoke.c"), "-L", os.path.join(ROOT, "acrobotics_b200"),
+         "-lacro_b200", "-L", f"{cuda}/lib64", "-lcudart", "-lm", "-o", str(exe)],
+        check=True)
+    assert exe.exists()

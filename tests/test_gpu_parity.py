@@ -387,3 +387,29 @@ def test_path_sweep_large(gpu):
     # an endpoint in collision implies the sweep is in collision
     start_hit = k.is_in_collision_batch(qs, scene)
     assert (hit | ~start_hit).all()
+
+
+# ------------------------------------------------------------------- the boundary from C
+def test_c_program_on_the_abi(gpu, tmp_path):
+    """examples/c_abi_smoke.c: a plain C program (no Python objects, no torch) builds the Kuka and
+    the README scene through include/acro_b200.h and reproduces README.md:94-96."""
+    import os
+    import shutil
+    import subprocess
+
+    from conftest import ROOT
+
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if gcc is None or not os.path.exists(f"{cuda}/include/cuda_runtime_api.h"):
+        pytest.skip("gcc / CUDA toolkit not available")
+    exe = tmp_path / "c_abi_smoke"
+    lib_dir = os.path.join(ROOT, "acrobotics_b200")
+    subprocess.run(
+        [gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", f"{cuda}/include",
+         os.path.join(ROOT, "examples", "c_abi_smoke.c"), "-L", lib_dir, "-lacro_b200",
+         "-L", f"{cuda}/lib64", "-lcudart", "-lm", "-o", str(exe)], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{lib_dir}:{cuda}/lib64:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "F F F F T T T T F F" in out.stdout
