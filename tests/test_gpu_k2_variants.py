@@ -394,3 +394,43 @@ def test_random_robots_and_scenes(gpu):
         qg = q[:20_000] + rng.uniform(-0.3, 0.3, (20_000, robot.ndof))
         call = lambda: robot.is_path_in_collision_discrete_batch(q[:20_000], qg, scene, 0.1)  # noqa: E731
         assert (_with_variant("simple", call) == _with_variant("filter", call)).all(), trial
+
+
+def test_concurrent_callers(gpu):
+    """Handles are immutable and the scratch of a call is stream ordered: several host threads
+    (ctypes drops the GIL) check different batches against the same robot / scene handles on
+    their own streams and get what a single caller gets."""
+    import threading
+
+    import torch
+
+    k = ab.Kuka()
+    scene = scene16()
+    scene.prepare(k)
+    k._handle()  # build the shared robot handle before the threads start
+    batches = [torch.from_numpy(random_configs(200_000 + 1000 * i, 6, seed=100 + i)).cuda()
+               for i in range(6)]
+    expected = [k.is_in_collision_batch(b, scene, packed=True).clone() for b in batches]
+    torch.cuda.synchronize()
+    results = [None] * len(batches)
+    errors = []
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    out = k.is_in_collision_batch(batches[i], scene, packed=True)
+                stream.synchronize()
+            results[i] = out
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(batches))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for got, exp in zip(results, expected):
+        assert torch.equal(got, exp)
