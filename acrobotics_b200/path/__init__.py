@@ -5,7 +5,7 @@ samplers of ``TolPositionPt`` / ``TolEulerPt`` (``path/path_pt.py``), ``create_g
 (``path/util.py:23-57``) and ``PathPt.to_joint_solutions`` (``path/path_pt_base.py:87-111``),
 the latter also batched over a whole path (``joint_solutions_csr``)."""
 from .path_pt import TolEulerPt, TolPositionPt, joint_solutions_csr, path_to_joint_solutions
-from .tolerance import NoTolerance, SymmetricTolerance, Tolerance
+from .ranges import NoTolerance, SymmetricTolerance, Tolerance
 from .util import create_grid, rpy_to_rot_mat
 
 __all__ = [

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _native, device
-from .tolerance import Tolerance
+from .ranges import Tolerance
 from .util import create_grid, rpy_to_rot_mat
 
 
