@@ -14,7 +14,7 @@ constexpr int kItemCap = 64;      // candidate pairs per warp and round
 #define ACRO_FILTER_MIN_CTAS 5
 #endif
 #ifndef ACRO_FILTER_DIRECT_MIN
-#define ACRO_FILTER_DIRECT_MIN 20
+#define ACRO_FILTER_DIRECT_MIN 28
 #endif
 constexpr int kSceneStrideF = 16; // floats per scene box: R2 row-major, T2, B, radius
 
