@@ -110,6 +110,38 @@ class TolEulerPt(_PathPt):
         return self.rel_to_abs(create_grid([tol.discretize() for tol in self.tol]))
 
 
+def _tolerance_key(pt):
+    return (type(pt), tuple((t.lower, t.upper, t.num_samples, t.has_tolerance) for t in pt.tol))
+
+
+def path_grid_arrays(path):
+    """Grid samples of a whole path without a Python loop per point: points of the same kind
+    with the same tolerances share their relative grid, so their (S, 4, 4) sample arrays are
+    one broadcast.  Returns a list of (indices, T) with T of shape (len(indices), S, 4, 4)."""
+    groups = {}
+    for i, pt in enumerate(path):
+        groups.setdefault(_tolerance_key(pt), []).append(i)
+    out = []
+    for idxs in groups.values():
+        first = path[idxs[0]]
+        if not isinstance(first, (TolPositionPt, TolEulerPt)):
+            out.append((idxs, np.stack([path[i].sample_grid_array() for i in idxs])))
+            continue
+        grid = create_grid([tol.discretize() for tol in first.tol]).astype(np.float64)  # (S, 3|6)
+        R = np.stack([path[i].rotation_matrix for i in idxs])                          # (P, 3, 3)
+        pos = np.stack([path[i].pos for i in idxs])                                    # (P, 3)
+        P, S = len(idxs), len(grid)
+        T = np.zeros((P, S, 4, 4))
+        T[..., 3, 3] = 1.0
+        T[..., :3, 3] = pos[:, None, :] + np.einsum("sj,pij->psi", grid[:, :3], R)
+        if isinstance(first, TolEulerPt):
+            T[..., :3, :3] = np.einsum("pij,sjk->psik", R, rpy_to_rot_mat(grid[:, 3:6]))
+        else:
+            T[..., :3, :3] = R[:, None]
+        out.append((idxs, T))
+    return out
+
+
 def joint_solutions_csr(robot, T, scene, return_all=False):
     """Planner inner loop for a whole path.
 
@@ -153,14 +185,9 @@ def joint_solutions_csr(robot, T, scene, return_all=False):
 def path_to_joint_solutions(path, robot, scene=None):
     """List of (M_i, ndof) arrays, one per path point (planning/sampling_based.py:94-106);
     raises like the reference when a point has no valid joint solution.  Points may have
-    different sample counts; they are grouped by count so that each group is one launch."""
-    grids = [pt.sample_grid_array() for pt in path]
+    different tolerances; points with the same tolerances form one launch."""
     out = [None] * len(path)
-    by_count = {}
-    for i, g in enumerate(grids):
-        by_count.setdefault(len(g), []).append(i)
-    for count, idxs in by_count.items():
-        T = np.stack([grids[i] for i in idxs])
+    for idxs, T in path_grid_arrays(path):
         q, off = joint_solutions_csr(robot, T, scene)
         for k, i in enumerate(idxs):
             out[i] = q[off[k]:off[k + 1]]

@@ -184,3 +184,32 @@ def test_workspace_envelope(gpu):
     exp = free.reshape(len(pts), -1).sum(axis=1) / (8 * 20)
     assert np.abs(got - exp).max() <= 1.0 / 160 + 1e-12  # at most one near-contact solution
     assert got.max() > 0.2 and got.min() == 0.0
+
+
+def test_planner_demo_end_to_end(gpu):
+    """examples/planner_demo.py at a small size: the joint path follows the line, is collision
+    free and continuous."""
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    spec_ = importlib.util.spec_from_file_location("planner_demo",
+                                                   os.path.join(ROOT, "examples", "planner_demo.py"))
+    demo = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(demo)
+    q_path, length, (robot, scene, path) = demo.plan(points=60, samples=24, verbose=False)
+    assert q_path.shape == (60, 6) and np.isfinite(length)
+    assert not robot.is_in_collision_batch(q_path, scene).any()
+    T = robot.fk_batch(q_path)
+    want = np.array([pt.pos for pt in path])
+    assert np.abs(T[:, :3, 3] - want).max() < 1e-9
+    # the same graph through the CPU DP: same cost, same joint path
+    from acrobotics_b200.path import joint_solutions_csr
+    from oracle import dp_oracle
+
+    T_grid = np.stack([pt.sample_grid_array() for pt in path])
+    q_free, off = joint_solutions_csr(robot, T_grid, scene)
+    ref = dp_oracle.shortest_path([q_free[off[i]:off[i + 1]] for i in range(len(path))], "sum_squared")
+    assert abs(ref["length"] - length) <= 1e-9 * max(1.0, length)
+    assert np.array_equal(np.array(ref["path"]), q_path)

@@ -54,3 +54,26 @@ def test_rpy_convention_inverts_fk_rpy_formula():
     assert np.allclose(np.arctan2(-R[:, 1, 2], R[:, 2, 2]), a[:, 0])
     assert np.allclose(np.arctan2(R[:, 0, 2], np.hypot(R[:, 0, 0], R[:, 0, 1])), a[:, 1])
     assert np.allclose(np.arctan2(-R[:, 0, 1], R[:, 0, 0]), a[:, 2])
+
+
+def test_path_grid_arrays_equal_per_point_grids():
+    from acrobotics_b200.path import path_grid_arrays
+
+    rng = np.random.default_rng(0)
+
+    def rot(a):
+        return rpy_to_rot_mat(np.array(a))
+
+    path = []
+    for k in range(7):
+        path.append(TolEulerPt(rng.normal(size=3), rot(rng.normal(size=3)),
+                               [SymmetricTolerance(0.1, 3), NoTolerance(), NoTolerance()],
+                               [NoTolerance(), SymmetricTolerance(0.5, 4), SymmetricTolerance(np.pi, 5)]))
+        path.append(TolPositionPt(rng.normal(size=3), rot(rng.normal(size=3)),
+                                  [SymmetricTolerance(0.1, 3), Tolerance(0.2, 1.0, 2), NoTolerance()]))
+    seen = set()
+    for idxs, T in path_grid_arrays(path):
+        for k, i in enumerate(idxs):
+            assert np.allclose(T[k], path[i].sample_grid_array(), atol=1e-14)
+            seen.add(i)
+    assert seen == set(range(len(path)))
