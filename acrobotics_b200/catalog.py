@@ -213,6 +213,19 @@ class KukaOnRail(Robot):
         super().__init__(_build(rail + _kuka_rows(a1, a2, d4, d6)))
         self.kuka = Kuka(a1=a1, a2=a2, d4=d4, d6=d6)
 
+    def ik_batch(self, T, q_fixed):
+        """Batched ``ik`` for one rail position: T (N,4,4) -> (q (N,8,7), valid (N,8)); the
+        first column of every solution is ``q_fixed``."""
+        Td = np.asarray(T, dtype=np.float64).reshape(-1, 4, 4)
+        Tw = tf_inverse(self.tf_base) @ Td
+        if self.tf_tool_tip is not None:
+            Tw = Tw @ tf_inverse(self.tf_tool_tip)
+        self.kuka.tf_base = self.links[0].get_link_relative_transform(q_fixed)
+        q6, valid = self.kuka.ik_batch(Tw)
+        q7 = np.concatenate([np.full(q6.shape[:2] + (1,), float(q_fixed)), q6], axis=2)
+        q7[~valid] = np.nan
+        return q7, valid
+
     def ik(self, T, q_fixed) -> IKResult:
         Tw = tf_inverse(self.tf_base) @ np.asarray(T, dtype=np.float64)
         if self.tf_tool_tip is not None:

@@ -336,6 +336,14 @@ def test_kuka_on_rail_ik(gpu):
     res = rail.ik(rail.fk(q), q[0])
     assert res.success
     assert min(np.abs(np.array(s) - q).max() for s in res.solutions) < 1e-6
+    # batched, one rail position: every valid branch reproduces its pose
+    qs = random_configs(2000, 7, seed=19)
+    qs[:, 0] = 0.4
+    T = rail.fk_batch(qs)
+    sol, valid = rail.ik_batch(T, 0.4)
+    assert sol.shape == (2000, 8, 7) and valid.any(axis=1).all()
+    back = rail.fk_batch(sol[valid])
+    assert np.abs(back - np.repeat(T, 8, axis=0).reshape(2000, 8, 4, 4)[valid]).max() < 1e-9
 
 
 # ------------------------------------------------------------------------ Jacobians
