@@ -103,9 +103,30 @@ template <>
 __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) {
   sincos(x, s, c);
 }
+// FP32 chain (poses good to 1e-5): Cody-Waite reduction by pi/2 in three exact steps and the
+// Cephes minimax polynomials on [-pi/4, pi/4] (abs error ~1.5e-7) for |x| <= 1024; the library
+// routine beyond that.  Half the instructions of sincosf and no slow-path stack frame.
 template <>
 __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) {
-  sincosf(x, s, c);
+  if (!(fabsf(x) <= 1024.0f)) {
+    sincosf(x, s, c);
+    return;
+  }
+  const float t = fmaf(x, 0.636619772f, 12582912.0f);  // 1.5 * 2^23: the integer lands in the mantissa
+  const int k = __float_as_int(t);
+  const float kf = t - 12582912.0f;
+  float r = fmaf(kf, -1.5703125f, x);
+  r = fmaf(kf, -4.837512969970703125e-4f, r);
+  r = fmaf(kf, -7.54978995489188216e-8f, r);
+  const float z = r * r;
+  float sp = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+  sp = fmaf(sp * z, r, r);
+  float cp = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+  cp = fmaf(cp * z, z, fmaf(-0.5f, z, 1.0f));
+  const float a = (k & 1) ? cp : sp;
+  const float b = (k & 1) ? sp : cp;
+  *s = (k & 2) ? -a : a;
+  *c = ((k + 1) & 2) ? -b : b;
 }
 
 template <typename real>
