@@ -13,6 +13,9 @@ constexpr int kItemCap = 64;      // candidate pairs per warp and round
 #ifndef ACRO_FILTER_MIN_CTAS
 #define ACRO_FILTER_MIN_CTAS 5
 #endif
+#ifndef ACRO_SAT_PRETEST
+#define ACRO_SAT_PRETEST 0
+#endif
 #ifndef ACRO_FILTER_DIRECT_MIN
 #define ACRO_FILTER_DIRECT_MIN 28
 #endif
@@ -46,12 +49,29 @@ __device__ __forceinline__ void sincos_filter(double q, float& s, float& c) {
 __device__ __forceinline__ int sat_filter(const float A0, const float A1, const float A2,
                                           const float* R1, const float* c1, const float* R2,
                                           const float* T2, const float B0, const float B1,
-                                          const float B2, const float delta) {
+                                          const float B2, const float delta, const float rA,
+                                          const float rB) {
   const float p0 = T2[0] - c1[0], p1 = T2[1] - c1[1], p2 = T2[2] - c1[2];
   const float A[3] = {A0, A1, A2};
   const float B[3] = {B0, B1, B2};
   float R[9], Q[9];
   float g = -1e30f;
+#if ACRO_SAT_PRETEST
+  // Cheap rejections before R = R1^T R2 is formed: a face axis of one box against the bounding
+  // sphere of the other.  sum_i |R_ij| A_i <= |A| <= rA (rounded up on the host), so
+  // |t_j| - (B_j + rA) is a lower bound of FCL's face-axis quantity; likewise for box 1's axes.
+  {
+    float ts[3], ps[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      ts[j] = fmaf(R2[6 + j], p2, fmaf(R2[3 + j], p1, R2[j] * p0));
+      ps[j] = fmaf(R1[6 + j], p2, fmaf(R1[3 + j], p1, R1[j] * p0));
+    }
+    const float gs = fmaxf(fmaxf(fmaxf(fabsf(ts[0]) - B0, fabsf(ts[1]) - B1), fabsf(ts[2]) - B2) - rA,
+                           fmaxf(fmaxf(fabsf(ps[0]) - A0, fabsf(ps[1]) - A1), fabsf(ps[2]) - A2) - rB);
+    if (gs > delta) return kSep;
+  }
+#endif
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -280,13 +300,14 @@ amb = false;
       // warp are redistributed over its lanes (items in a shared-memory list, the owner's
       // pose fetched with shuffles) so that the 15-axis test still runs on dense warps.
       auto load_other = [&](int other, int owner, float* R2, float* T2, float& B0, float& B1,
-                            float& B2) {
+                            float& B2, float& rB) {
         if (other < 64) {
           const float* ob = s_scene + other * kSceneStrideF;
 #pragma unroll
           for (int e = 0; e < 9; ++e) R2[e] = ob[e];
           T2[0] = ob[9]; T2[1] = ob[10]; T2[2] = ob[11];
           B0 = ob[12]; B1 = ob[13]; B2 = ob[14];
+          rB = ob[15];
         } else {
           const int sl = other - 64;
           const float* sv = s_saved + sl * 12 * 32 + owner;
@@ -294,6 +315,7 @@ amb = false;
           for (int e = 0; e < 9; ++e) R2[e] = sv[e * 32];
           T2[0] = sv[9 * 32]; T2[1] = sv[10 * 32]; T2[2] = sv[11 * 32];
           B0 = s_half[4 * sl]; B1 = s_half[4 * sl + 1]; B2 = s_half[4 * sl + 2];
+          rB = s_half[4 * sl + 3];
         }
       };
       for (;;) {
@@ -311,9 +333,9 @@ amb = false;
               other = 64 + __ffs((int)mself) - 1;
               mself &= mself - 1;
             }
-            float R2[9], T2[3], B0, B1, B2;
-            load_other(other, (int)lane, R2, T2, B0, B1, B2);
-            const int res = sat_filter(A0, A1, A2, Rw, cw, R2, T2, B0, B1, B2, delta);
+            float R2[9], T2[3], B0, B1, B2, rB;
+            load_other(other, (int)lane, R2, T2, B0, B1, B2, rB);
+            const int res = sat_filter(A0, A1, A2, Rw, cw, R2, T2, B0, B1, B2, delta, bx.radius, rB);
             if (res == kHit) {
               hit = true;
               done = true;
@@ -359,9 +381,9 @@ amb = false;
           const bool owner_done = __shfl_sync(kFull, (int)done, owner) != 0;
           int res = kSep;
           if (valid && !owner_done) {
-            float R2[9], T2[3], B0, B1, B2;
-            load_other(other, owner, R2, T2, B0, B1, B2);
-            res = sat_filter(A0, A1, A2, R1, c1, R2, T2, B0, B1, B2, delta);
+            float R2[9], T2[3], B0, B1, B2, rB;
+            load_other(other, owner, R2, T2, B0, B1, B2, rB);
+            res = sat_filter(A0, A1, A2, R1, c1, R2, T2, B0, B1, B2, delta, bx.radius, rB);
           }
           const unsigned hb = __reduce_or_sync(kFull, res == kHit ? (1u << owner) : 0u);
           const unsigned ab = __reduce_or_sync(kFull, res == kAmb ? (1u << owner) : 0u);

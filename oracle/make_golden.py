@@ -19,6 +19,13 @@ boxbox.npz       Shape.is_in_collision known answers (tests/test_shapes.py:128-1
                  tests/test_geometry.py:42-59) and random pairs.
 jac.npz          central-difference Jacobians of the verbatim fk / fk_rpy (the
                  method of reference tests/test_jacobians.py; casadi is absent).
+cc_kuka_10k.npz  SURVEY 8(d)'s ">= 10 k against the verbatim path": 10 000 random Kuka
+                 configurations against the 16-box benchmark scene and the README scene
+                 plus self-collision verdicts, all through the reference's own
+                 Robot.is_in_collision (``python -m oracle.make_golden cc10k``).
+polyhedron.npz   Box.get_polyhedron (A, b) of random boxes (shapes.py:163-172): pins
+                 oracle/lp_boxbox.py, the FCL-independent Box-Box ground truth
+                 (``python -m oracle.make_golden polyhedron``).
 
 The Box-Box predicate inside those verdicts is oracle/fcl_boxbox.py (python-fcl is
 not installable here); everything else is the reference's own code.
@@ -55,9 +62,59 @@ def _num_jac(fun, q, h=1e-5):
     return J
 
 
+def _cc10k_chunk(args):
+    """Worker: verdicts of the verbatim reference for one chunk of configurations."""
+    q, = args
+    ab = ref_shim.load_reference()
+    kuka = ab.Kuka()
+    s16_sides, s16_tfs = scene16_spec(0)
+    s16 = _ref_scene(ab, s16_sides, s16_tfs)
+    readme = _ref_scene(ab, np.array([[2, 2, 0.1], [0.2, 0.2, 1.5]]),
+                        np.array([translation(0, 0, -0.2), translation(0, 0.5, 0.55)]))
+    return (np.array([kuka.is_in_collision(x, s16) for x in q]),
+            np.array([kuka.is_in_collision(x, readme) for x in q]),
+            np.array([kuka.is_in_self_collision(x) for x in q]))
+
+
+def make_cc10k(n=10_000, seed=20241020):
+    """10 000 configurations through the verbatim Robot.is_in_collision (robot.py:244-273)."""
+    import multiprocessing as mp
+
+    q = np.random.default_rng(seed).uniform(-np.pi, np.pi, (n, 6))
+    cores = min(8, os.cpu_count() or 1)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        parts = pool.map(_cc10k_chunk, [(c,) for c in np.array_split(q, cores * 4)])
+    np.savez_compressed(
+        os.path.join(GOLDEN, "cc_kuka_10k.npz"), seed=seed, q=q,
+        hit_scene16=np.packbits(np.concatenate([p[0] for p in parts])),
+        hit_readme=np.packbits(np.concatenate([p[1] for p in parts])),
+        hit_self=np.packbits(np.concatenate([p[2] for p in parts])),
+    )
+
+
+def make_polyhedron(n=200, seed=7):
+    ab = ref_shim.load_reference()
+    rng = np.random.default_rng(seed)
+    sides = rng.uniform(0.01, 2.0, (n, 3))
+    tfs = np.array([pose_z(rng.uniform(-3, 3), *rng.uniform(-2, 2, 3)) @ pose_x(rng.uniform(-3, 3), 0, 0, 0)
+                    @ pose_z(rng.uniform(-3, 3), 0, 0, 0) for _ in range(n)])
+    A, b = [], []
+    for s, tf in zip(sides, tfs):
+        poly = ab.Box(*s).get_polyhedron(tf)
+        A.append(np.array(poly.A))
+        b.append(np.array(poly.b))
+    np.savez(os.path.join(GOLDEN, "polyhedron.npz"), sides=sides, tf=tfs, A=np.array(A), b=np.array(b))
+
+
 def main():
     ab = ref_shim.load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    if "cc10k" in sys.argv[1:] or "polyhedron" in sys.argv[1:]:
+        if "cc10k" in sys.argv[1:]:
+            make_cc10k()
+        if "polyhedron" in sys.argv[1:]:
+            make_polyhedron()
+        return
     rng = np.random.default_rng(20240601)
 
     # ---------------- FK ----------------
@@ -278,6 +335,8 @@ def main():
         out[f"{name}_jpos"] = np.array([_num_jac(lambda x: r.fk(x)[:3, 3].copy(), x) for x in q])
         out[f"{name}_jrpy"] = np.array([_num_jac(lambda x: r.fk_rpy(x), x) for x in q])
     np.savez(os.path.join(GOLDEN, "jac.npz"), **out)
+    make_cc10k()
+    make_polyhedron()
     print("golden vectors written to", GOLDEN)
 
 

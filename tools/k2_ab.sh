@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: tools/k2_ab.sh <out.jsonl> <tag> [<tag> ...]   ("default" = libacro_b200.so)
+out=$1; shift
+: > "$out"
+for t in "$@"; do
+  if [ "$t" = default ]; then unset ACRO_B200_LIB; else export ACRO_B200_LIB=$PWD/acrobotics_b200/libacro_b200_$t.so; fi
+  python tools/k2_quick.py --tag "$t" >> "$out" 2>> "${out%.jsonl}.err"
+done
+cat "$out"
