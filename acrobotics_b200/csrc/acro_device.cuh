@@ -201,6 +201,45 @@ __device__ __forceinline__ void tf_mul_dh(Tf<real>& T, real ct, real st, real ca
   }
 }
 
+// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two FP32 lanes per instruction, one operand may
+// be a scalar broadcast).  The helpers keep the operation order of the scalar code, so results
+// are bit-identical to it.
+#ifndef ACRO_F32X2
+#define ACRO_F32X2 1
+#endif
+__device__ __forceinline__ float2 mul2(float s, float2 v) { return __fmul2_rn(make_float2(s, s), v); }
+__device__ __forceinline__ float2 fma2(float s, float2 v, float2 acc) {
+  return __ffma2_rn(make_float2(s, s), v, acc);
+}
+
+#if ACRO_F32X2
+// rows 0 and 1 of every column as one packed lane pair, row 2 scalar: 20 instead of 30 issue slots
+template <>
+__device__ __forceinline__ void tf_mul_dh<float>(Tf<float>& T, float ct, float st, float ca,
+                                                 float sa, float a, float d) {
+  const float2 c0 = make_float2(T.r[0], T.r[3]), c1 = make_float2(T.r[1], T.r[4]),
+               c2 = make_float2(T.r[2], T.r[5]);
+  const float2 u = fma2(st, c1, mul2(ct, c0));
+  const float2 w = fma2(ct, c1, mul2(-st, c0));
+  const float2 n1 = fma2(sa, c2, mul2(ca, w));
+  const float2 n2 = fma2(ca, c2, mul2(-sa, w));
+  const float2 pn = fma2(d, c2, fma2(a, u, make_float2(T.p[0], T.p[1])));
+  T.r[0] = u.x; T.r[3] = u.y;
+  T.r[1] = n1.x; T.r[4] = n1.y;
+  T.r[2] = n2.x; T.r[5] = n2.y;
+  T.p[0] = pn.x; T.p[1] = pn.y;
+  {
+    const float r0 = T.r[6], r1 = T.r[7], r2 = T.r[8];
+    const float us = fmaf(r1, st, r0 * ct);
+    const float ws = fmaf(r1, ct, -(r0 * st));
+    T.r[6] = us;
+    T.r[7] = fmaf(r2, sa, ws * ca);
+    T.r[8] = fmaf(r2, ca, -(ws * sa));
+    T.p[2] = fmaf(d, r2, fmaf(a, us, T.p[2]));
+  }
+}
+#endif
+
 // out = T * M  (M is a 3x4 constant from the descriptor)
 template <typename real>
 __device__ __forceinline__ void tf_mul(Tf<real>& out, const Tf<real>& T, const real* m) {

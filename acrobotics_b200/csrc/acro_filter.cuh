@@ -19,7 +19,11 @@ constexpr int kItemCap = 64;      // candidate pairs per warp and round
 #ifndef ACRO_FILTER_DIRECT_MIN
 #define ACRO_FILTER_DIRECT_MIN 28
 #endif
-constexpr int kSceneStrideF = 16; // floats per scene box: R2 row-major, T2, B, radius
+constexpr int kSceneStrideF = 16; // floats per scene box in shared memory, see kScenePerm
+// Shared-memory order of a scene box: the rotation is stored as the lane pairs the packed SAT
+// consumes - (R00,R01) (R10,R11) (R20,R21) then R02 R12 R22 - so that 16-byte loads drop every
+// pair into an aligned register pair; then T2 [9..11], half extents [12..14], radius [15].
+__device__ __constant__ const int kScenePerm[16] = {0, 1, 3, 4, 6, 7, 2, 5, 8, 9, 10, 11, 12, 13, 14, 15};
 
 enum : int { kSep = 0, kHit = 1, kAmb = 2 };
 
@@ -72,6 +76,57 @@ __device__ __forceinline__ int sat_filter(const float A0, const float A1, const 
     if (gs > delta) return kSep;
   }
 #endif
+#if ACRO_F32X2
+  // columns 0 and 1 of R = R1^T R2 as packed lane pairs (FFMA2 with a scalar-broadcast operand),
+  // column 2 scalar; same operation order as the scalar form below, hence the same bits
+  const float2 r2p0 = make_float2(R2[0], R2[1]), r2p1 = make_float2(R2[3], R2[4]),
+               r2p2 = make_float2(R2[6], R2[7]);
+  float2 Rp[3], Qp[3];
+  float Rs[3], Qs[3];
+  (void)R; (void)Q;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Rp[i] = fma2(R1[6 + i], r2p2, fma2(R1[3 + i], r2p1, mul2(R1[i], r2p0)));
+    Rs[i] = fmaf(R1[6 + i], R2[8], fmaf(R1[3 + i], R2[5], R1[i] * R2[2]));
+    Qp[i] = make_float2(fabsf(Rp[i].x), fabsf(Rp[i].y));
+    Qs[i] = fabsf(Rs[i]);
+  }
+  {
+    const float2 tp = fma2(p2, r2p2, fma2(p1, r2p1, mul2(p0, r2p0)));
+    const float ts = fmaf(R2[8], p2, fmaf(R2[5], p1, R2[2] * p0));
+    const float2 radp = __fadd2_rn(fma2(A2, Qp[2], fma2(A1, Qp[1], mul2(A0, Qp[0]))),
+                                   make_float2(B0, B1));
+    const float rads = fmaf(Qs[2], A2, fmaf(Qs[1], A1, Qs[0] * A0)) + B2;
+    g = fmaxf(g, fmaxf(fmaxf(fabsf(tp.x) - radp.x, fabsf(tp.y) - radp.y), fabsf(ts) - rads));
+  }
+  if (g > delta) return kSep;
+  float pp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pp[i] = fmaf(R1[6 + i], p2, fmaf(R1[3 + i], p1, R1[i] * p0));
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    g = fmaxf(g, fabsf(pp[i]) - (fmaf(Qs[i], B2, fmaf(Qp[i].y, B1, Qp[i].x * B0)) + A[i]));
+  if (g > delta) return kSep;
+  const float2 fudge = make_float2(1.0e-6f, 1.0e-6f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Qp[i] = __fadd2_rn(Qp[i], fudge);
+    Qs[i] += 1.0e-6f;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    const float2 tp = fma2(pp[i2], Rp[i1], mul2(-pp[i1], Rp[i2]));
+    const float ts = fmaf(pp[i2], Rs[i1], -(pp[i1] * Rs[i2]));
+    // box 2's share of the radius: B[j1] Q[i][j2] + B[j2] Q[i][j1] for j = 0, 1, 2
+    const float in0 = fmaf(B1, Qs[i], B2 * Qp[i].y);
+    const float in1 = fmaf(B2, Qp[i].x, B0 * Qs[i]);
+    const float in2 = fmaf(B0, Qp[i].y, B1 * Qp[i].x);
+    const float2 radp = fma2(A[i1], Qp[i2], fma2(A[i2], Qp[i1], make_float2(in0, in1)));
+    const float rads = fmaf(A[i1], Qs[i2], fmaf(A[i2], Qs[i1], in2));
+    g = fmaxf(g, fmaxf(fmaxf(fabsf(tp.x) - radp.x, fabsf(tp.y) - radp.y), fabsf(ts) - rads));
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -107,6 +162,7 @@ __device__ __forceinline__ int sat_filter(const float A0, const float A1, const 
       g = fmaxf(g, fabsf(t) - rad);
     }
   }
+#endif
   if (g > delta) return kSep;
   return g < -delta ? kHit : kAmb;
 }
@@ -170,7 +226,7 @@ __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
   float* s_half = s_scene + sc.n * kSceneStrideF + warps * n_saved * 12 * 32;
   for (int k = threadIdx.x; k < sc.n * kSceneStrideF; k += blockDim.x) {
     const int j = k >> 4, e = k & 15;
-    s_scene[k] = sc.boxes[j * kSceneStride + e];
+    s_scene[k] = sc.boxes[j * kSceneStride + kScenePerm[e]];
   }
   for (int b = threadIdx.x; b < rb.n_boxes; b += blockDim.x) {
     const int sl = rb.boxes[b].save_slot;
@@ -303,8 +359,9 @@ amb = false;
                             float& B2, float& rB) {
         if (other < 64) {
           const float* ob = s_scene + other * kSceneStrideF;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) R2[e] = ob[e];
+          R2[0] = ob[0]; R2[1] = ob[1]; R2[3] = ob[2]; R2[4] = ob[3];
+          R2[6] = ob[4]; R2[7] = ob[5]; R2[2] = ob[6]; R2[5] = ob[7];
+          R2[8] = ob[8];
           T2[0] = ob[9]; T2[1] = ob[10]; T2[2] = ob[11];
           B0 = ob[12]; B1 = ob[13]; B2 = ob[14];
           rB = ob[15];
