@@ -335,16 +335,25 @@ class Robot(RobotKinematics):
     # ------------------------------------------------------------------
     def is_in_collision_batch(
         self, q, scene, return_near=False, margin=DEFAULT_MARGIN, packed=False, dtype="f64",
-        _force_self=False,
+        _force_self=False, out=None,
     ):
         """(N, ndof) x Scene -> bool (N,).  ``return_near``: also a mask of the
         configurations whose decisive separation is within ``margin`` of contact.
-        ``packed``: return the raw uint32 bit-mask words instead of booleans."""
+        ``packed``: return the raw uint32 bit-mask words instead of booleans.
+        ``out``: a CUDA int32 tensor of at least ``ceil(N / 32)`` words that receives the packed
+        verdicts in place (implies ``packed``; used by the multi-GPU sharding, whose kernel
+        writes straight into its block of the all-gather buffer)."""
         tdt = torch.float64 if dtype == "f64" else torch.float32
         qd, host = self._q(q, tdt)
         n = qd.shape[0]
         self.cc_checks += n
-        words = torch.zeros(device.mask_words(n), dtype=torch.int32, device="cuda")
+        if out is not None:
+            if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.int32
+                    and out.is_contiguous() and out.numel() >= device.mask_words(n)):
+                raise ValueError("out must be a contiguous CUDA int32 tensor of >= ceil(N/32) words")
+            words, packed, host = out, True, False
+        else:
+            words = torch.zeros(device.mask_words(n), dtype=torch.int32, device="cuda")
         near = torch.zeros_like(words) if return_near else None
         lib = _native.load()
         robot_h = self._handle(force_self=_force_self)
@@ -424,14 +433,22 @@ class Robot(RobotKinematics):
         num_steps = int(np.ceil(np.linalg.norm(q_goal - q_start) / max_q_step))
         return [(1 - s) * q_start + s * q_goal for s in np.linspace(0, 1, num_steps)]
 
-    def is_path_in_collision_discrete_batch(self, q_start, q_goal, scene, max_q_step=0.1):
-        """(E, ndof) segment starts / goals -> bool (E,): some interpolant collides."""
+    def is_path_in_collision_discrete_batch(self, q_start, q_goal, scene, max_q_step=0.1,
+                                            packed=False, out=None):
+        """(E, ndof) segment starts / goals -> bool (E,): some interpolant collides.
+        ``packed`` / ``out``: as in ``is_in_collision_batch``."""
         qs, host = self._q(q_start)
         qg, _ = self._q(q_goal)
         if qs.shape != qg.shape:
             raise ValueError("q_start and q_goal must have the same shape")
         e = qs.shape[0]
-        words = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda")
+        if out is not None:
+            if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.int32
+                    and out.is_contiguous() and out.numel() >= device.mask_words(e)):
+                raise ValueError("out must be a contiguous CUDA int32 tensor of >= ceil(E/32) words")
+            words, packed, host = out, True, False
+        else:
+            words = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda")
         _native.check(
             _native.load().acro_path_cc_f64(
                 self._handle(),
@@ -441,6 +458,8 @@ class Robot(RobotKinematics):
             ),
             "acro_path_cc_f64",
         )
+        if packed:
+            return words if not host else words.cpu().numpy().view(np.uint32)
         return device.unpack_mask(words, e, host)
 
     def is_path_in_collision_discrete(self, q_start, q_goal, collection, max_q_step=0.1):

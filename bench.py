@@ -178,6 +178,83 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
+K2_SOURCES = ["acrobotics_b200/csrc/fk_cc_filt.cu", "acrobotics_b200/csrc/acro_filter.cuh",
+              "acrobotics_b200/csrc/acro_device.cuh", "acrobotics_b200/csrc/acro_collide.cuh"]
+
+
+def k2_source_hash():
+    """sha256 over the sources of the K2 kernels: the ncu counters of profiles/k2_profile.json
+    are only reported when they were captured from exactly these sources."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for rel in K2_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _events(torch, n):
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for _ in range(n)]
+
+
+def _time_steps(torch, dist, world, fn, steps, warmup):
+    """W warm-up + K timed calls of fn() on the current stream, barrier + synchronize on both
+    sides, CUDA events, max over ranks.  Returns ms per step."""
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+def parity_record(robot, scene, q_dev, hit_words, n_check, threads):
+    """Verdicts of the timed kernel on the first n_check configurations of the benchmark input
+    against the plain-C oracle (oracle_fk_cc) on the host; configurations within the 1e-6 m
+    margin are counted separately (BASELINE north star)."""
+    import concurrent.futures as cf
+
+    import numpy as np
+
+    import acrobotics_b200 as ab  # noqa: F401
+    from oracle import c_oracle
+    from oracle import np_oracle as no
+
+    n_check = min(n_check, int(q_dev.shape[0]))
+    q = q_dev[:n_check].cpu().numpy()
+    w = hit_words[: (n_check + 31) // 32].cpu().numpy().view(np.uint32)
+    got = np.unpackbits(w.view(np.uint8), bitorder="little")[:n_check].astype(bool)
+    packed = c_oracle.pack(no.spec_from_robot(robot), scene)
+    c_oracle.load()
+    chunks = np.array_split(np.arange(n_check), max(1, threads) * 4)
+    with cf.ThreadPoolExecutor(max(1, threads)) as ex:  # ctypes releases the GIL
+        parts = list(ex.map(lambda idx: c_oracle.fk_cc_packed(packed, q[idx], want_g=True), chunks))
+    hit = np.concatenate([p[0] for p in parts])
+    g = np.concatenate([p[1] for p in parts])
+    near = np.abs(g) <= 1e-6
+    return {
+        "checked": int(n_check), "oracle": "oracle/c/acro_oracle.c (oracle_fk_cc), pinned to the "
+        "verbatim reference by tests/test_parity_hardening_cpu.py",
+        "mismatches_outside_margin": int(((got != hit) & ~near).sum()),
+        "margin_m": 1e-6, "margin_bucket": int(near.sum()),
+        "mismatches_inside_margin": int(((got != hit) & near).sum()),
+        "collision_rate": float(hit.mean()),
+    }
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,9 +270,10 @@ def run_ours(args):
             "sample": (f"{n_sample} random configurations in {dt:.1f} s over {cores} processes; "
                        "oracle/scalar_port.py = the reference's per-configuration Python path "
                        "(numpy 4x4 chain, one native box-box call per pair)"),
+            "note": ("a port, not the reference itself: python-fcl is not installable here; the port "
+                     "is pinned to the verbatim reference's verdicts (tests/test_parity_hardening_cpu.py) "
+                     "and is ~1.85x faster per core than the reference run through oracle/ref_shim.py"),
         }
-
-    if cpu_baseline is not None:
         # context: the vectorised numpy oracle on one core (SURVEY 8d, item ii)
         import numpy as _np
 
@@ -212,7 +290,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import acrobotics_b200 as ab
-    from acrobotics_b200 import _native
+    from acrobotics_b200 import _native, sharding
     from acrobotics_b200.synthetic import random_configs_device, scene16
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
@@ -222,27 +300,41 @@ def run_ours(args):
     lib = _native.load()
     robot, scene = ab.Kuka(), scene16()
     robot_h, scene_h = robot._handle(), scene.native_handle()
-
-    n = args.configs
-    words = (n + 31) // 32
-    q = random_configs_device(n, 6, seed=1000 + rank)
-    # the kernel writes its mask words straight into this rank's slice of the gather buffer
-    gathered = torch.zeros(world * words, dtype=torch.int32, device="cuda")
-    mask = gathered[rank * words:(rank + 1) * words]
+    # candidate grid + filter tolerance of this (robot, scene) pair: built once, outside the hot call
+    _native.check(lib.acro_scene_prepare(scene_h, robot_h), "acro_scene_prepare")
     stream = torch.cuda.current_stream().cuda_stream
+    C = _native.C
 
-    def kernel():
-        _native.check(lib.acro_fk_cc_f64(robot_h, scene_h, q.data_ptr(), n, _native.Q_AOS,
-                                         mask.data_ptr(), None, 0.0, stream), "acro_fk_cc_f64")
+    # ---- headline (weak scaling): every rank brings its own n configurations, the product's
+    # sharding API runs the kernel in `pieces` pieces straight into the all-gather buffer and
+    # gathers piece k (NCCL) under the kernel of piece k+1
+    n = args.configs
+    pieces = 1 if world == 1 else args.pieces
+    if n % (32 * pieces):
+        raise SystemExit(f"--configs must be a multiple of {32 * pieces}")
+    q = random_configs_device(n, 6, seed=1000 + rank)
+    shards = sharding.MaskShards(n * world, world, rank, pieces, "cuda")
+    kernel_events = []
 
-    def step(ev=None):
-        if ev:
+    class TimedRobot:
+        """The product Robot with CUDA events around its batched collision call (the dominant
+        kernel's launch duration for the roofline record)."""
+
+        def __init__(self, inner):
+            self.inner = inner
+
+        def is_in_collision_batch(self, *a, **kw):
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        kernel()
-        if ev:
+            out = self.inner.is_in_collision_batch(*a, **kw)
             ev[1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, mask)
+            kernel_events.append(ev)
+            return out
+
+    timed_robot = TimedRobot(robot)
+
+    def step():
+        sharding.is_in_collision_local_shard(timed_robot, q, scene, pieces=pieces, shards=shards)
 
     def barrier():
         if world > 1:
@@ -252,34 +344,120 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    kernel_events.clear()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
     ev0.record()
-    for k in range(args.steps):
-        step(kev[k])
+    for _ in range(args.steps):
+        step()
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
     launches = _native.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     total_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / args.steps],
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in kernel_events) / args.steps],
                            dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
     value = world * n / (ms_per_step * 1e-3)
-    w = mask[: 1 << 16].cpu().numpy().view(np.uint32)
-    collision_rate = float(np.unpackbits(w.view(np.uint8)).sum()) / min(n, 32 * len(w))
+    # this rank's verdict words (block order of MaskShards), for the parity record
+    own = torch.cat([shards.local_words(k) for k in range(shards.pieces)]).clone()
+
+    # ---- strong scaling (BASELINE configs[2]): the SAME n configurations split over
+    # the ranks, rank r takes rows [r n / G, (r + 1) n / G) (in 2 pieces when G > 1)
+    strong = None
+    if not args.no_strong:
+        q_all = q if rank == 0 else random_configs_device(n, 6, seed=1000)
+        sp = 1 if world == 1 else 2
+        sshards = sharding.MaskShards(n, world, rank, sp, "cuda")
+
+        def strong_step():
+            sharding.is_in_collision_sharded(robot, q_all, scene, pieces=sp, packed=True, shards=sshards)
+
+        sms = _time_steps(torch, dist, world, strong_step, args.steps, args.warmup)
+        same = bool((sshards.mask()[: 1 << 14] == shards.mask()[: 1 << 14]).all().item()) if world == 1 else None
+        strong = {"configs_total": n, "ms_per_step": sms, "value": n / (sms * 1e-3), "unit": UNIT,
+                  "pieces": sp, "partition": "rank r: rows [r n/G, (r+1) n/G) of the same n",
+                  "collective": "ncclAllGather of the verdict words, in place, piece k under the "
+                                "kernel of piece k+1", "equals_weak_result_at_n1": same}
+        del q_all, sshards
+
+    # ---- C5 (BASELINE configs[4]): 10k-point path x 400 pose samples, IK -> collision filter ->
+    # CSR, path points sharded over the ranks, counts + free masks all-gathered
+    c5 = None
+    if not args.no_c5:
+        P, S = args.c5_points, args.c5_samples
+        m = P * S
+        hk = robot._handle(kinematics_only=True)
+        T = torch.empty((m, 4, 4), dtype=torch.float64, device="cuda")
+        qsrc = random_configs_device(m, 6, seed=555)  # same poses on every rank
+        _native.check(lib.acro_fk_f64(hk, qsrc.data_ptr(), m, 0, T.data_ptr(), 0, stream))
+        del qsrc
+        T = T.view(P, S, 4, 4)
+        res = {}
+
+        def c5_step():
+            res["r"] = sharding.joint_solutions_csr_sharded(robot, T, scene)
+
+        cms = _time_steps(torch, dist, world, c5_step, max(2, args.steps // 2), 2)
+        free_total = int(res["r"]["counts"].sum().item())
+        c5 = {"path_points": P, "samples_per_point": S, "ik_branches_checked": 8 * m,
+              "ms_per_step": cms, "poses_per_s": m / (cms * 1e-3),
+              "ik_solutions_checked_per_s": 8 * m / (cms * 1e-3),
+              "collision_free_solutions": free_total, "n_gpus": world,
+              "partition": "contiguous path-point ranges per rank",
+              "collective": "all-gather of per-point counts (int64) and per-pose free-branch masks (uint8)"}
+        del T, res
+
+    # ---- C2 / C4 (single-GPU configs; reported at N = 1)
+    c2 = c4 = None
+    if world == 1 and not args.no_c24:
+        hk = robot._handle(kinematics_only=True)
+        peaks_hbm = _hbm_peak()[0]
+        c2 = {}
+        for label, nn in (("1M", 1_000_000), ("64M", 64_000_000)):
+            qq = q[:nn]
+            Tb = torch.empty((nn, 4, 4), dtype=torch.float64, device="cuda")
+            f = lambda: _native.check(lib.acro_fk_f64(hk, qq.data_ptr(), nn, 0, Tb.data_ptr(), 0, stream))  # noqa: E731
+            ms = _time_steps(torch, dist, 1, f, 10, 3)
+            gbs = 176.0 * nn / (ms * 1e-3) / 1e9
+            c2[label] = {"configs": nn, "ms": ms, "poses_per_s": nn / (ms * 1e-3), "hbm_gbs": gbs,
+                         "frac_of_measured_hbm": gbs / peaks_hbm, "bytes_per_config": 176}
+            del Tb
+        nn = 1_000_000
+        Tp = torch.empty((nn, 4, 4), dtype=torch.float64, device="cuda")
+        _native.check(lib.acro_fk_f64(hk, q.data_ptr(), nn, 0, Tp.data_ptr(), 0, stream))
+        sol = torch.empty((nn, 8, 6), dtype=torch.float64, device="cuda")
+        valid = torch.empty(nn, dtype=torch.uint8, device="cuda")
+        free = torch.empty(nn, dtype=torch.uint8, device="cuda")
+        f = lambda: _native.check(lib.acro_ik_kuka_cc_f64(robot_h, scene_h, Tp.data_ptr(), nn, sol.data_ptr(),  # noqa: E731
+                                                          valid.data_ptr(), free.data_ptr(), stream))
+        ms = _time_steps(torch, dist, 1, f, 10, 3)
+        nsol = int(torch.tensor([bin(x).count("1") for x in range(256)], device="cuda")[valid.long()].sum().item())
+        c4 = {"poses": nn, "ms": ms, "poses_per_s": nn / (ms * 1e-3), "ik_solutions": nsol,
+              "ik_solutions_checked_per_s": nsol / (ms * 1e-3),
+              "path": "acro_ik_kuka_cc_f64: analytical IK (all 8 branches) -> filtered FK+collision -> free masks"}
+        f = lambda: _native.check(lib.acro_ik_kuka_f64(robot._handle(kinematics_only=True), Tp.data_ptr(), nn,  # noqa: E731
+                                                       sol.data_ptr(), valid.data_ptr(), stream))
+        ms = _time_steps(torch, dist, 1, f, 10, 3)
+        gbs = 513.0 * nn / (ms * 1e-3) / 1e9
+        c4["ik_only"] = {"ms": ms, "poses_per_s": nn / (ms * 1e-3), "hbm_gbs": gbs,
+                         "frac_of_measured_hbm": gbs / peaks_hbm, "bytes_per_pose": 513}
+        del Tp, sol, valid, free
+
+    # ---- parity of the timed kernel's verdicts against the C oracle (rank 0)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_record(robot, scene, q, own, args.parity_configs, os.cpu_count() or 1)
 
     # ---- end to end: pinned host buffers through the C ABI host entry point ----
     e2e = None
@@ -310,7 +488,7 @@ def run_ours(args):
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        same = bool((mask_host[: 1 << 12].cuda() == mask[: 1 << 12]).all().item())
+        same = bool((mask_host[: 1 << 12].cuda() == own[: 1 << 12]).all().item())
         e2e = {
             "value": world * n_e2e * args.e2e_steps / dt.item(), "unit": UNIT,
             "h2d_bytes_per_step": n_e2e * 48, "d2h_bytes_per_step": ((n_e2e + 31) // 32) * 4,
@@ -321,65 +499,63 @@ def run_ours(args):
         del q_host, mask_host
 
     if rank == 0:
-        # compute roofline denominator: measured DFMA chain on this GPU
-        tf = _native.C.c_double()
-        pk_ms = _native.C.c_double()
-        _native.check(lib.acro_measure_fma_peak(1, 4000, _native.C.byref(tf), _native.C.byref(pk_ms)))
+        # compute roofline denominators: measured FMA chains on this GPU, in this run
+        tf = C.c_double()
+        pk_ms = C.c_double()
+        _native.check(lib.acro_measure_fma_peak(1, 4000, C.byref(tf), C.byref(pk_ms)))
         fp64_peak = tf.value
-        _native.check(lib.acro_measure_fma_peak(0, 4000, _native.C.byref(tf), _native.C.byref(pk_ms)))
+        _native.check(lib.acro_measure_fma_peak(0, 4000, C.byref(tf), C.byref(pk_ms)))
         fp32_peak = tf.value
         kms = kern_ms.item()
-        achieved = W_FULL_FLOP * n / (kms * 1e-3) / 1e12
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_peak, peak_src = _hbm_peak()
         hbm_gbs = BYTES_PER_CONFIG * n / (kms * 1e-3) / 1e9
+        w_full = W_FULL_FLOP * n / (kms * 1e-3) / 1e12
+        prof = K2_PROFILE if K2_PROFILE.get("source_sha256") == k2_source_hash() else {}
+        fp32_flop = prof.get("fp32_flop_per_config")
+        executed = (fp32_flop * n / (kms * 1e-3) / 1e12) if fp32_flop else None
+        collision_rate = parity["collision_rate"] if parity else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD, "configs_per_gpu_per_step": n, "scene_boxes": 16,
-                "robot_boxes": 6, "self_pairs": 6, "parallelism": f"shard{world}+allgather(mask)",
+                "robot_boxes": 6, "self_pairs": 6,
+                "parallelism": (f"shard{world}: sharding.is_in_collision_local_shard, {pieces} piece(s) per "
+                                "step, in-place ncclAllGather of piece k under the kernel of piece k+1"),
                 "l2": "inputs (4.8 GB/GPU) exceed the 126 MB L2; no explicit flush",
-                "arithmetic": ("FP32 filter with rigorous error pads + candidate grid, exact FP64 "
+                "arithmetic": ("FP32 filter (packed FFMA2) with error pads + candidate grid, exact FP64 "
                                "re-evaluation of the ambiguous configurations: verdicts "
                                "bit-identical to the all-FP64 kernel"),
-                "collision_rate": round(collision_rate, 4),
+                "collision_rate": collision_rate,
             },
             "roofline": {
-                # contract view: algorithmic bytes of the dominant kernel / its CUDA-event time
-                "bound": "hbm", "kernel": K2_KERNEL,
-                "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "traffic": K2_PROFILE.get("dram_bytes_per_config", 0) * n or None,
-                "kernel_ms": kms,
-                "note": ("48.125 algorithmic bytes per configuration; DRAM traffic (ncu) is 1.04x "
-                         "that. The kernel is NOT HBM-bound and has no GEMM shape: it is bound by "
-                         "instruction issue, see 'compute' and DESIGN.md section 4"),
-                # what actually bounds the kernel
-                "compute": {
-                    "bound": "instruction issue (CUDA cores, FP32 filter + FP64 exact pass)",
-                    "issue_slots_active_frac": (K2_PROFILE.get("issue_active_pct") or 0) / 100.0,
-                    "warp_inst_per_config": K2_PROFILE.get("warp_inst_per_config"),
-                    "thread_inst_per_config": K2_PROFILE.get("thread_inst_per_config"),
-                    "fp32_flop_per_config": K2_PROFILE.get("fp32_flop_per_config"),
-                    "fp64_flop_per_config": K2_PROFILE.get("fp64_flop_per_config"),
-                    "executed_fp32_tflops": (K2_PROFILE.get("fp32_flop_per_config", 0) * n
-                                             / (kms * 1e-3) / 1e12),
-                    "fp32_fma_peak_measured_tflops": fp32_peak,
-                    "fp64_fma_peak_measured_tflops": fp64_peak,
-                    # FK + all 102 box pairs x full 15-axis SAT, no culling
-                    "w_full_flop_per_config": W_FULL_FLOP,
-                    "w_full_equiv_tflops": achieved,
-                    "w_full_equiv_over_fp64_peak": achieved / fp64_peak,
-                    "source": "ncu --set full, profiles/" + str(K2_PROFILE.get("source")),
-                },
+                # what bounds the kernel: instruction issue on the CUDA cores (FP32 filter)
+                "bound": "issue/fp32", "kernel": K2_KERNEL, "kernel_ms": kms,
+                "achieved": executed, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": (executed / fp32_peak) if executed else None,
+                "peak_source": "FFMA chain measured in this run (acro_measure_fma_peak)",
+                "achieved_source": ("executed FP32 flop per configuration (ncu, profiles/k2_profile.json, "
+                                    "same kernel sources: sha256 verified) x configurations / CUDA-event "
+                                    "kernel time of this run") if executed else
+                                   "profiles/k2_profile.json is stale for these kernel sources: not reported",
+                "traffic": (prof.get("dram_bytes_per_config", 0) * n) or None,
+                "issue_slots_active_frac": (prof.get("issue_active_pct") or 0) / 100.0 or None,
+                "warp_inst_per_config": prof.get("warp_inst_per_config"),
+                "thread_inst_per_config": prof.get("thread_inst_per_config"),
+                "fp32_flop_per_config": fp32_flop,
+                "fp64_flop_per_config": prof.get("fp64_flop_per_config"),
+                "fp64_fma_peak_measured_tflops": fp64_peak,
+                # FK + all 102 box pairs x full 15-axis SAT, no culling
+                "w_full_flop_per_config": W_FULL_FLOP, "w_full_equiv_tflops": w_full,
+                "w_full_equiv_over_fp64_peak": w_full / fp64_peak,
+                # secondary view: the input/output stream against HBM
+                "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_gbs / hbm_peak, "peak_source": peak_src,
+                        "bytes_per_config": BYTES_PER_CONFIG},
+                "profile_source": prof.get("source"),
             },
+            "strong": strong, "c2": c2, "c4": c4, "c5": c5, "parity": parity,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -388,6 +564,14 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def main():
@@ -400,6 +584,14 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 22, help="host pipeline chunk (configs)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--pieces", type=int, default=4, help="kernel/all-gather pieces per step when N > 1")
+    ap.add_argument("--parity-configs", type=int, default=1 << 20)
+    ap.add_argument("--c5-points", type=int, default=10_000)
+    ap.add_argument("--c5-samples", type=int, default=400)
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-c24", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -18,19 +18,35 @@ MARGIN = 1e-6
 IK_TOL = 1e-9
 
 
-def _assert_ik_parity(sol, ref, valid, what):
-    """IK solution sets within 1e-9, except solutions at a wrist singularity
-    (|sin q5| < 1e-3), where the closed form itself amplifies rounding by
-    1/|sin q5| (numpy float64 differs from a long-double evaluation by 1.5e-8
-    there): those get a tolerance scaled by the conditioning and are counted."""
+def _assert_ik_parity(sol, ref, valid, what, spec_for_fk=None, T=None):
+    """IK solution sets within 1e-9 (BASELINE north star) - no widened tolerance.  Solutions at
+    a wrist singularity (|sin q5| < 1e-3) are the one place where the closed form itself is
+    ill-conditioned (q4 and q6 are individually determined only to rounding / |sin q5|; numpy
+    float64 differs from a long-double evaluation by 1.5e-8 there): they are COUNTED and
+    REPORTED, held to the 1e-9 bound on the well-conditioned quantities (q1..q3, q5 and the
+    pose they reproduce) and excluded from the per-joint bound on q4 / q6 only."""
     err = np.abs(sol - ref)
     err[~valid] = 0.0
     s5 = np.abs(np.sin(np.where(valid, ref[..., 4], 1.0)))
-    tol = IK_TOL * np.maximum(1.0, 1e-3 / np.maximum(s5, 1e-12))
-    assert (err.max(axis=-1) <= tol).all(), f"{what}: worst {err.max():.3e}"
     singular = valid & (s5 < 1e-3)
+    regular = valid & ~singular
+    worst_regular = err[regular].max(initial=0.0)
+    assert worst_regular <= IK_TOL, f"{what}: worst regular solution {worst_regular:.3e}"
+    n_sing = int(singular.sum())
+    worst_pose = 0.0
+    if n_sing:
+        assert err[singular][:, [0, 1, 2]].max() <= IK_TOL, what
+        if spec_for_fk is not None:
+            idx = np.nonzero(singular)
+            pose = no.fk(spec_for_fk, sol[idx])
+            worst_pose = float(np.abs(pose - T[idx[0]]).max())
+            # the pose error is first order in the q4/q6 rounding times |sin q5| <= 1e-3
+            assert worst_pose <= 1e-9, f"{what}: singular solutions reproduce the pose to {worst_pose:.3e}"
+    print(f"[ik-parity] {what}: {int(valid.sum())} solutions, worst |dq| {worst_regular:.2e} on the "
+          f"regular ones; {n_sing} wrist-singular solutions (|sin q5| < 1e-3) reported separately, "
+          f"worst |dq4,dq6| {err[singular].max(initial=0.0):.2e}, worst pose error {worst_pose:.2e}")
     assert singular.mean() < 5e-3, what
-    return int(singular.sum())
+    return n_sing
 
 
 def _assert_collision_parity(gpu_hit, gpu_near, g_oracle, what):
@@ -195,20 +211,82 @@ def test_collision_tool_base_rail(gpu):
     assert (rail.is_in_collision_batch(g["rail_q"], scene16()) == g["rail_hit_scene16"]).all()
 
 
+def _c_oracle_margins(robot, scene, q, threads=None):
+    """hit, g of the plain-C oracle over all rows of q (threads: ctypes releases the GIL)."""
+    import concurrent.futures as cf
+    import os
+
+    from oracle import c_oracle
+
+    packed = c_oracle.pack(spec(robot), scene)
+    c_oracle.load()
+    threads = threads or (os.cpu_count() or 1)
+    chunks = np.array_split(np.arange(len(q)), threads * 4)
+    with cf.ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda idx: c_oracle.fk_cc_packed(packed, q[idx], want_g=True), chunks))
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
 def test_collision_one_million_vs_oracle(gpu):
-    """1 M random configurations against the 16-box scene: bit-exact outside the
-    1e-6 m bucket, bucket reported."""
+    """>= 1 M random configurations against the oracle, 16-box scene: bit-exact
+    outside the 1e-6 m bucket, bucket reported.  All 1 M against the plain-C oracle, the first
+    200 k against the vectorised numpy oracle as well."""
     k = ab.Kuka()
     scene = scene16()
     q = random_configs(1_000_000, 6, seed=1)
     hit, near = k.is_in_collision_batch(q, scene, return_near=True)
     assert (k.is_in_collision_batch(q, scene) == hit).all()
+    c_hit, c_g = _c_oracle_margins(k, scene, q)
+    assert (c_hit == ~(c_g > 0)).all()
+    _assert_collision_parity(hit, near, c_g, "scene16 1M vs C oracle")
+    print(f"[cc-parity] scene16 1M: 0 mismatches outside the margin, "
+          f"{int((np.abs(c_g) <= MARGIN).sum())} configurations inside +-{MARGIN:g} m, "
+          f"{int(near.sum())} flagged by the kernel")
     gq = no.collision_margins(spec(k), scene, q[:200_000])
-    _assert_collision_parity(hit[:200_000], near[:200_000], gq, "scene16 200k")
+    _assert_collision_parity(hit[:200_000], near[:200_000], gq, "scene16 200k vs numpy oracle")
+    assert np.abs(gq - c_g[:200_000]).max() < 1e-12  # the two restatements agree on the margin
     assert 0.5 < hit.mean() < 0.95
     # packed words and booleans describe the same set
     words = k.is_in_collision_batch(q, scene, packed=True)
     assert np.unpackbits(words.view(np.uint8), bitorder="little")[: len(q)].sum() == hit.sum()
+
+
+def test_collision_bench_inputs_vs_c_oracle(gpu):
+    """The benchmark's own generator and seed (bench.py: random_configs_device(n, 6, 1000)):
+    the first 1 M configurations of the timed input against the C oracle, self-collision-only
+    and README scene included."""
+    from acrobotics_b200.synthetic import random_configs_device
+
+    k = ab.Kuka()
+    qd = random_configs_device(1 << 20, 6, seed=1000)
+    q = qd.cpu().numpy()
+    for scene, label in ((scene16(), "scene16"), (readme_scene(), "readme")):
+        hit, near = k.is_in_collision_batch(qd, scene, return_near=True)
+        hit, near = hit.cpu().numpy(), near.cpu().numpy()
+        _, c_g = _c_oracle_margins(k, scene, q)
+        _assert_collision_parity(hit, near, c_g, f"bench input {label}")
+    hit = k.is_in_self_collision_batch(qd).cpu().numpy()
+    _, c_g = _c_oracle_margins(k, None, q)
+    assert ((hit == ~(c_g > 0)) | (np.abs(c_g) <= MARGIN)).all()
+
+
+def test_collision_verbatim_reference_10k(gpu):
+    """>= 10 k configurations against the VERBATIM reference's verdicts."""
+    g = golden("cc_kuka_10k.npz")
+    k = ab.Kuka()
+    q = g["q"]
+    n = len(q)
+    assert n >= 10_000
+    for scene, key in ((scene16(), "hit_scene16"), (readme_scene(), "hit_readme")):
+        want = np.unpackbits(g[key])[:n].astype(bool)
+        hit, near = k.is_in_collision_batch(q, scene, return_near=True)
+        assert not near.any(), "a golden configuration sits inside the margin bucket"
+        assert (hit == want).all(), key
+    want = np.unpackbits(g["hit_self"])[:n].astype(bool)
+    assert (k.is_in_self_collision_batch(q) == want).all()
+    # scalar API on a few of them
+    for i in (0, 17, 4242):
+        assert k.is_in_collision(q[i], scene16()) == bool(np.unpackbits(g["hit_scene16"])[i])
 
 
 def test_collision_properties_and_edges(gpu):
@@ -220,8 +298,13 @@ def test_collision_properties_and_edges(gpu):
     # ragged batch sizes: every prefix gives the prefix of the result
     for n in (1, 31, 32, 33, 127, 128, 129, 1000):
         assert (k.is_in_collision_batch(q[:n], scene) == full[:n]).all()
-    # joint angles are periodic: q + 2*pi gives the same verdict
-    assert (k.is_in_collision_batch(q + 2 * np.pi, scene) == full).mean() > 0.9999
+    # joint angles are periodic: q + 2*pi gives the same verdict (q + 2 pi is rounded, i.e. the
+    # angle moves by ~4e-16 rad: only a configuration inside the margin bucket may change)
+    shifted, near_s = k.is_in_collision_batch(q + 2 * np.pi, scene, return_near=True)
+    _, near_0 = k.is_in_collision_batch(q, scene, return_near=True)
+    assert ((shifted == full) | near_s | near_0).all()
+    print(f"[cc-parity] periodicity: {int((shifted != full).sum())} of {len(q)} verdicts changed, "
+          f"all inside the margin bucket ({int((near_s | near_0).sum())} configurations)")
     # permutation equivariance
     perm = np.random.default_rng(0).permutation(len(q))
     assert (k.is_in_collision_batch(q[perm], scene) == full[perm]).all()
@@ -268,7 +351,7 @@ def test_ik_one_million_vs_oracle(gpu):
     assert valid.any(1).all()
     o_sol, o_valid = no.ik_kuka(s, T[:100_000])
     assert (o_valid == valid[:100_000]).all()
-    _assert_ik_parity(sol[:100_000], o_sol, o_valid, "ik 100k")
+    _assert_ik_parity(sol[:100_000], o_sol, o_valid, "ik 100k", spec_for_fk=s, T=T[:100_000])
     # round trip on the full batch: fk(ik(T)) == T.  The reference asserts 5 decimals on a
     # handful of poses (tests/test_inverse_kinematics.py:120); its elbow snap (|c3| > 1 - 1e-6
     # -> +-1, arm_2.py:41-43) moves q3 by up to 1.4e-3 rad, so over 1 M poses the bound is looser
@@ -390,8 +473,23 @@ def test_path_sweep_large(gpu):
     qs = rng.uniform(-np.pi, np.pi, (20_000, 6))
     qg = qs + rng.uniform(-0.4, 0.4, qs.shape)
     hit = k.is_path_in_collision_discrete_batch(qs, qg, scene, 0.1)
-    ora = no.is_path_in_collision_discrete(spec(k), scene, qs[:300], qg[:300], 0.1)
-    assert (hit[:300] == ora).mean() > 0.99  # interpolants within 1e-6 of contact may differ
+    # oracle with margin bookkeeping: a segment is robust when none of its interpolants is
+    # within 1e-6 m of contact; robust segments must agree exactly, the rest is counted
+    m = 2000
+    s_ = spec(k)
+    robust = np.ones(m, bool)
+    ora = np.zeros(m, bool)
+    for e in range(m):
+        P = np.array(no.interpolation_path(qs[e], qg[e], 0.1)).reshape(-1, 6)
+        if len(P):
+            gq = no.collision_margins(s_, scene, P)
+            ora[e] = bool((gq <= 0).any())
+            robust[e] = bool((np.abs(gq) > MARGIN).all())
+    assert (hit[:m][robust] == ora[robust]).all()
+    print(f"[cc-parity] path sweep: {int(robust.sum())} robust segments agree exactly, "
+          f"{int((~robust).sum())} segments have an interpolant inside the margin bucket "
+          f"({int((hit[:m][~robust] != ora[~robust]).sum())} of them differ)")
+    assert (~robust).mean() < 5e-3
     # an endpoint in collision implies the sweep is in collision
     start_hit = k.is_in_collision_batch(qs, scene)
     assert (hit | ~start_hit).all()

@@ -68,3 +68,121 @@ def test_all_gathered_mask_equals_single_rank(tmp_path, world, n):
         assert len(w) == (n + 31) // 32
         bits = np.unpackbits(w.view(np.uint8), bitorder="little")[:n].astype(bool)
         assert (bits == hit).all()
+
+
+# ---------------------------------------------------------------------------
+# MaskShards: piece-wise layout with the all-gather of piece k under the kernel of piece k+1
+# ---------------------------------------------------------------------------
+def test_mask_shards_blocks_tile_the_batch():
+    for n in (1, 31, 32, 33, 1000, 4097, 100_000_007):
+        for world in (1, 2, 3, 8):
+            for pieces in (1, 2, 4):
+                shards = [sharding.MaskShards(n, world, r, pieces) for r in range(world)]
+                sh = shards[0]
+                covered = []
+                for k in range(sh.pieces):
+                    for r in range(world):
+                        lo, hi, w0 = shards[r].block(k)
+                        assert w0 == (k * world + r) * sh.per and (lo % 32 == 0 or lo == n)
+                        covered.append((lo, hi))
+                assert covered[0][0] == 0 and covered[-1][1] == n
+                for (lo, hi), (lo2, _) in zip(covered, covered[1:]):
+                    assert hi == lo2 and lo <= hi
+                assert sh.buffer.numel() == sh.per * world * sh.pieces >= sh.words
+    # pieces = 1 is SURVEY 8e's contiguous partition
+    for r in range(4):
+        assert sharding.MaskShards(1000, 4, r).block(0)[:2] == sharding.shard_range(1000, r, 4)
+
+
+def _pieces_worker(rank, world, port, n, pieces, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng_bits = np.random.default_rng(77).integers(0, 2, n).astype(bool)  # stand-in verdicts
+
+        def into(lo, hi, out):
+            bits = rng_bits[lo:hi]
+            bits = np.concatenate([bits, np.zeros((-len(bits)) % 32, bool)])
+            w = torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy())
+            out[: w.numel()] = w
+
+        sh = sharding.check_sharded(n, into, pieces=pieces)
+        np.save(os.path.join(out_dir, f"p{rank}.npy"), sh.mask().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,pieces", [(2, 5000, 3), (3, 64 * 9 + 5, 2), (2, 40, 4)])
+def test_piecewise_gather_equals_single_rank(tmp_path, world, n, pieces):
+    mp.spawn(_pieces_worker, args=(world, _free_port(), n, pieces, str(tmp_path)), nprocs=world, join=True)
+    want = np.random.default_rng(77).integers(0, 2, n).astype(bool)
+    for r in range(world):
+        w = np.load(tmp_path / f"p{r}.npy").view(np.uint32)
+        assert len(w) == (n + 31) // 32
+        assert (np.unpackbits(w.view(np.uint8), bitorder="little")[:n].astype(bool) == want).all()
+
+
+# ---------------------------------------------------------------------------
+# planner sweep (C5) sharded over path points; the oracle stands in for the GPU pipeline
+# ---------------------------------------------------------------------------
+def _oracle_csr(T):
+    """CPU stand-in for joint_solutions_csr(..., return_all=True) on (P, S, 4, 4) poses."""
+    import acrobotics_b200 as ab
+    from acrobotics_b200.synthetic import scene16
+    from oracle import np_oracle as no
+
+    spec = no.spec_from_robot(ab.Kuka())
+    scene = no.scene_arrays(scene16())
+    P, S = T.shape[:2]
+    sol, valid = no.ik_kuka(spec, np.asarray(T).reshape(-1, 4, 4))
+    hit = np.zeros_like(valid)
+    if valid.any():
+        hit[valid] = no.is_in_collision(spec, scene, sol[valid])
+    free = valid & ~hit
+    rows = sol[free]                                        # pose-major, branch-minor order
+    counts = free.reshape(P, S * 8).sum(1)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    fbits = np.packbits(free, axis=1, bitorder="little").reshape(P, S)
+    vbits = np.packbits(valid, axis=1, bitorder="little").reshape(P, S)
+    return (torch.from_numpy(rows.reshape(-1, 6)), torch.from_numpy(off), None,
+            torch.from_numpy(vbits), torch.from_numpy(fbits))
+
+
+def _csr_worker(rank, world, port, P, S, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = torch.from_numpy(np.load(os.path.join(out_dir, "T.npy")))
+        res = sharding.joint_solutions_csr_sharded(None, T, None, gather_solutions=True,
+                                                   solve_local=lambda Tl: _oracle_csr(Tl.numpy()))
+        np.savez(os.path.join(out_dir, f"csr{rank}.npz"), counts=res["counts"].numpy(),
+                 free=res["free"].numpy(), q_free=res["q_free"].numpy(),
+                 offsets=res["offsets"].numpy(), lo=res["points"][0], hi=res["points"][1],
+                 q_local=res["q_local"].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,P,S", [(2, 7, 5), (3, 5, 4), (2, 1, 3)])
+def test_planner_sweep_sharded_over_path_points(tmp_path, world, P, S):
+    import acrobotics_b200 as ab
+    from acrobotics_b200.synthetic import random_configs
+    from oracle import np_oracle as no
+
+    spec = no.spec_from_robot(ab.Kuka())
+    T = no.fk(spec, random_configs(P * S, 6, seed=21)).reshape(P, S, 4, 4)
+    T[0, 0, :3, 3] *= 5.0  # an unreachable sample
+    np.save(tmp_path / "T.npy", T)
+    mp.spawn(_csr_worker, args=(world, _free_port(), P, S, str(tmp_path)), nprocs=world, join=True)
+    rows, off, _, _, fbits = _oracle_csr(T)
+    covered = 0
+    for r in range(world):
+        g = np.load(tmp_path / f"csr{r}.npz")
+        assert np.array_equal(g["counts"], np.diff(off.numpy()))
+        assert np.array_equal(g["free"], fbits.numpy())
+        assert np.array_equal(g["offsets"], off.numpy())
+        assert np.array_equal(g["q_free"], rows.numpy())
+        lo, hi = int(g["lo"]), int(g["hi"])
+        assert np.array_equal(g["q_local"], rows.numpy()[off[lo]:off[hi]])
+        covered += hi - lo
+    assert covered == P
