@@ -439,7 +439,7 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
       }
     });
     uint32_t* amb = nullptr;
-    e = cudaMallocAsync(&amb, sizeof(uint32_t) * ((n + 31) / 32), st);
+    e = cudaMallocAsync(&amb, filter_scratch_bytes(n), st);
     if (e != cudaSuccess) return e;
     GridView view = plan->view;
     view.skip_nan = skip_nan ? 1 : 0;

@@ -35,8 +35,10 @@ cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, 
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
-                                uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
+                                uint32_t* mask, uint32_t* scratch, uint32_t* near_mask,
                                 double margin, int split_slot, cudaStream_t st);
+// bytes of `scratch` for a batch of n configurations (ambiguity mask + the chunk counter)
+size_t filter_scratch_bytes(int64_t n);
 
 cudaError_t launch_fk_cc_fixup(const RobotDev<double>& rb64, SceneView<double> sc64, const double* q,
                                int64_t n, int layout, uint32_t* mask, const uint32_t* amb_mask,

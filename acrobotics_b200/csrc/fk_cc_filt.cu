@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved, const int split_slot,
                         const unsigned early_mask, const double* __restrict__ q, const int64_t n, const int layout,
-                        uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask) {
+                        uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask,
+                        unsigned long long* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [q buffers: 4 warps x 2 x 32*NDOF doubles (prefetch double buffer; pass 2 borrows the idle one)]
   // [stash: 4 warps x 64 int64][filter context]
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   __syncthreads();
 
   const int64_t n_chunks = (n + 31) >> 5;
+#if !ACRO_FILTER_DYNAMIC
   const int64_t stride = (int64_t)gridDim.x * kWarps;
+#endif
 
   // asynchronous copy of one chunk's joint values into buffer `buf` (flat for AoS,
   // joint-major for SoA)
@@ -125,7 +128,21 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   // pass 1 has just finished with: that buffer is only refilled by the next pass-1 iteration
   int stashed = 0;                   // warp-uniform
   int it = 0;
+#if ACRO_FILTER_DYNAMIC
+  // Chunks are handed out by a grid-wide counter (one atomic per chunk, fetched one iteration
+  // ahead so that its latency hides behind the chunk being processed): the cost of a chunk
+  // varies a lot (pass 2, candidate rounds), and with a static stride the slowest warp of a
+  // small batch finishes long after the average one.
+  auto grab = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(work_counter, 1ull);
+    return (int64_t)__shfl_sync(kFull, v, 0);
+  };
+  int64_t chunk = grab();
+  int64_t chunk_next = grab();
+#else
   int64_t chunk = (int64_t)blockIdx.x * kWarps + warp;
+#endif
   prefetch(chunk, 0);
   for (;;) {
     const bool second = split_slot > 0 && (stashed >= 32 || (chunk >= n_chunks && stashed > 0));
@@ -152,7 +169,11 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
       slot_end = -1;
     } else {
       const int buf = it & 1;
+#if ACRO_FILTER_DYNAMIC
+      prefetch(chunk_next, buf ^ 1);
+#else
       prefetch(chunk + stride, buf ^ 1);
+#endif
       cp_async_wait<1>();
       idx = (chunk << 5) + lane;
       act = idx < n;
@@ -186,7 +207,12 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
         if (cont) s_stash[stashed + __popc(cm & ((1u << lane) - 1u))] = (long long)idx;
         stashed += __popc(cm);
       }
+#if ACRO_FILTER_DYNAMIC
+      chunk = chunk_next;
+      chunk_next = chunk_next < n_chunks ? grab() : chunk_next;
+#else
       chunk += stride;
+#endif
       ++it;
     }
     __syncwarp();  // buffers, stash entries and this chunk's mask words are settled
@@ -330,6 +356,11 @@ cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, 
 // ---------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------
+size_t filter_scratch_bytes(int64_t n) {
+  const size_t words = (size_t)((n + 31) / 32);
+  return ((words * sizeof(uint32_t) + 7) / 8) * 8 + 8;
+}
+
 size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
   const int warps = kFThreads / 32;
   return sizeof(double) * warps * 2 * 32 * ndof + sizeof(long long) * warps * 64 +
@@ -350,9 +381,17 @@ static int persistent_blocks(K kern, size_t smem) {
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,
-                                uint32_t* mask, uint32_t* amb_mask, uint32_t* near_mask,
+                                uint32_t* mask, uint32_t* scratch, uint32_t* near_mask,
                                 double margin, int split_slot, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  // scratch: ambiguity mask words, then (8-byte aligned) the chunk counter of the filter kernel
+  uint32_t* amb_mask = scratch;
+  unsigned long long* work_counter = reinterpret_cast<unsigned long long*>(
+      reinterpret_cast<unsigned char*>(scratch) + filter_scratch_bytes(n) - 8);
+  {
+    cudaError_t e0 = cudaMemsetAsync(work_counter, 0, 8, st);
+    if (e0 != cudaSuccess) return e0;
+  }
   const int64_t tiles = (n + kFThreads - 1) / kFThreads;
   int n_saved = 0;
   for (int b = 0; b < rb32.n_boxes; ++b)
@@ -373,7 +412,8 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
       }
       const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
       kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, split_slot,
-                                                      early_mask, q, n, layout, mask, amb_mask);
+                                                      early_mask, q, n, layout, mask, amb_mask,
+                                                      work_counter);
       return cudaSuccess;
     };
     const bool prism = rb32.prismatic_mask != 0;

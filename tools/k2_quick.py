@@ -21,12 +21,13 @@ from acrobotics_b200.synthetic import random_configs_device, scene16  # noqa: E4
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=100_000_000)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--seed", type=int, default=1000)
 ap.add_argument("--tag", default=os.path.basename(os.environ.get("ACRO_B200_LIB", "default")))
 args = ap.parse_args()
 lib = _native.load()
 robot, scene = ab.Kuka(), scene16()
 n = args.n
-q = random_configs_device(n, 6, seed=1000)
+q = random_configs_device(n, 6, seed=args.seed)
 mask = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 rh, sh = robot._handle(), scene.native_handle()
