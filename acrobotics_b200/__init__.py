@@ -20,9 +20,19 @@ from .catalog import (
 )
 from .chain import DHLink, JointType, Link
 from .model import IKResult, JointLimit, Robot, RobotKinematics, Tool
+# path construction and planner settings (reference __init__.py:41-54)
+from .path import (FreeOrientationPt, NoTolerance, QuaternionTolerance, SampleMethod,
+                   SamplingSetting, SearchStrategy, SymmetricTolerance, Tolerance, TolEulerPt,
+                   TolPositionPt, TolQuatPt, create_arc, create_circle, create_line)
+from .planning import (CostFuntionType, OptSettings, PlanningSetup, SolveMethod, SolverSettings,
+                       solve)
 
 __all__ = [
-    "AnthropomorphicArm", "Arm2", "Box", "DHLink", "IKResult", "JointLimit", "JointType",
-    "Kuka", "KukaOnRail", "Link", "PlanarArm", "Robot", "RobotKinematics", "Scene",
-    "SphericalArm", "SphericalWrist", "Tool",
+    "AnthropomorphicArm", "Arm2", "Box", "CostFuntionType", "DHLink", "FreeOrientationPt",
+    "IKResult", "JointLimit", "JointType", "Kuka", "KukaOnRail", "Link", "NoTolerance",
+    "OptSettings", "PlanarArm", "PlanningSetup", "QuaternionTolerance", "Robot",
+    "RobotKinematics", "SampleMethod", "SamplingSetting", "Scene", "SearchStrategy",
+    "SolveMethod", "SolverSettings", "SphericalArm", "SphericalWrist", "SymmetricTolerance",
+    "Tolerance", "TolEulerPt", "TolPositionPt", "TolQuatPt", "Tool", "create_arc",
+    "create_circle", "create_line", "solve",
 ]

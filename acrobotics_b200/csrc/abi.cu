@@ -37,6 +37,7 @@ struct CullPlan {
   int mask_bits;
   void* cells;
   GridView view;
+  cudaEvent_t ready;   // recorded after the grid build; consumers on other streams wait on it
   int device;          // the grid lives in this device's memory
   int pins;            // host threads between get_plan and the end of their launches
   uint64_t last_use;   // for eviction (a scene keeps at most kMaxPlans plans)
@@ -276,8 +277,11 @@ struct PlanPin {  // RAII holder
 };
 
 // create = false: only look an existing plan up (*out stays nullptr when there is none)
+// A new plan is built on stream `st` (no device-wide synchronisation); every consumer makes its
+// stream wait on the plan's `ready` event, so a plan found by another thread / stream while its
+// grid is still being filled is safe to use.
 cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullPlan** out,
-                     bool create = true) {
+                     bool create = true, cudaStream_t st = nullptr) {
   std::lock_guard<std::mutex> lock(scene->mu);
   static std::atomic<uint64_t> clock{0};
   int dev = 0;
@@ -296,7 +300,7 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
       ++p->pins;
       p->last_use = ++clock;
       *out = p;
-      return cudaSuccess;
+      return p->ready ? cudaStreamWaitEvent(st, p->ready, 0) : cudaSuccess;
     }
   }
   if (!create) {
@@ -312,6 +316,7 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
         victim = k;
     if (victim == scene->plans.size()) break;  // everything is in use: grow instead
     cudaFree(scene->plans[victim]->cells);
+    if (scene->plans[victim]->ready) cudaEventDestroy(scene->plans[victim]->ready);
     delete scene->plans[victim];
     scene->plans.erase(scene->plans.begin() + victim);
   }
@@ -326,6 +331,7 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   p->dim = grid_dim_setting();
   p->mask_bits = scene->n <= 32 ? 32 : 64;
   p->cells = nullptr;
+  p->ready = nullptr;
   // FP32 filter tolerance.  Every SAT quantity is the result of O(100) FP32 operations on
   // numbers bounded by the workspace size P (unit roundoff 6e-8, sin/cos good to 1.2e-7, six
   // chained links): a first-order worst case is ~6e-6 P.  Measured over 4 M configurations x
@@ -350,20 +356,19 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   cudaError_t e = cudaSuccess;
   if (scene->n > 0 && p->n_classes > 0) {
     const size_t cells = (size_t)p->dim * p->dim * p->dim * p->n_classes;
-    double* d_rad = nullptr;
+    // one allocation per (robot geometry, scene) pair, on first use or in acro_scene_prepare;
+    // the class radii travel as a kernel parameter, the build is ordered on `st`
     e = cudaMalloc(&p->cells, cells * (p->mask_bits / 8));
-    if (e == cudaSuccess) e = cudaMalloc(&d_rad, sizeof(double) * p->n_classes);
-    if (e == cudaSuccess)
-      e = cudaMemcpy(d_rad, p->class_radius, sizeof(double) * p->n_classes, cudaMemcpyHostToDevice);
     // pad: half diagonal of a cell + FP32 position error + index rounding slack
     const double pad = 0.5 * cell * std::sqrt(3.0) * (1.0 + 1e-6) + delta + 1e-3 * cell;
     if (e == cudaSuccess)
       e = launch_build_grid(SceneView<double>{scene->dev64, scene->n}, p->cells, p->mask_bits,
-                            p->dim, p->n_classes, origin, cell, d_rad, pad, nullptr);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(d_rad);
+                            p->dim, p->n_classes, origin, cell, p->class_radius, pad, st);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(p->ready, st);
     if (e != cudaSuccess) {
       cudaFree(p->cells);
+      if (p->ready) cudaEventDestroy(p->ready);
       delete p;
       return e;
     }
@@ -410,14 +415,15 @@ constexpr int64_t kPlanMinBatch = 1 << 16;
 cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q,
                           int64_t n, int layout, uint32_t* mask, cudaStream_t st,
                           bool skip_nan = false, uint32_t* near_mask = nullptr,
-                          double margin = 0.0) {
+                          double margin = 0.0, void* workspace = nullptr,
+                          size_t workspace_bytes = 0) {
   const int variant = k2_variant();
   bool filtered = (variant >= 3 || skip_nan) && n >= kFilterMinBatch;
   const CullPlan* plan = nullptr;
   static const AcroScene empty_scene{};
   PlanPin pin;
   if (filtered) {
-    cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan, n >= kPlanMinBatch);
+    cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan, n >= kPlanMinBatch, st);
     if (e != cudaSuccess) return e;
     if (!plan) filtered = false;
     pin.scene = scene ? scene : &empty_scene;
@@ -438,9 +444,17 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
       }
     });
+    // scratch (ambiguity mask + chunk counter): the caller's workspace when it is large enough
+    // (acro_fk_cc_f64_ws: no allocation in the hot call), else stream-ordered pool memory
     uint32_t* amb = nullptr;
-    e = cudaMallocAsync(&amb, filter_scratch_bytes(n), st);
-    if (e != cudaSuccess) return e;
+    const bool own_scratch = !(workspace && workspace_bytes >= filter_scratch_bytes(n) &&
+                               (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0);
+    if (own_scratch) {
+      e = cudaMallocAsync(&amb, filter_scratch_bytes(n), st);
+      if (e != cudaSuccess) return e;
+    } else {
+      amb = static_cast<uint32_t*>(workspace);
+    }
     GridView view = plan->view;
     view.skip_nan = skip_nan ? 1 : 0;
     if (near_mask) {
@@ -451,7 +465,7 @@ cudaError_t run_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const 
       e = launch_fk_cc_filter(robot->d32, robot->d64, view, plan->mask_bits,
                               view_of<float>(scene), view_of<double>(scene), q, n, layout, mask,
                               amb, near_mask, margin, k2_split_slot(robot, scene), st);
-    cudaError_t e2 = cudaFreeAsync(amb, st);
+    cudaError_t e2 = own_scratch ? cudaFreeAsync(amb, st) : cudaSuccess;
     return e != cudaSuccess ? e : e2;
   }
   if (near_mask || variant >= 2 || (variant == 0 && !wave_supports(robot->d64)))
@@ -614,6 +628,7 @@ void acro_scene_destroy(AcroScene* scene) {
   if (!scene) return;
   for (CullPlan* p : scene->plans) {
     cudaFree(p->cells);
+    if (p->ready) cudaEventDestroy(p->ready);
     delete p;
   }
   cudaFree(scene->dev64);
@@ -623,9 +638,13 @@ void acro_scene_destroy(AcroScene* scene) {
 
 int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot) {
   if (!scene || !robot) return fail(ACRO_E_INVALID, "NULL handle");
+  if (int rc = check_scene_device(scene)) return rc;
   const CullPlan* plan = nullptr;
-  const cudaError_t e = get_plan(robot, scene, &plan);
-  if (e == cudaSuccess) release_plan(scene, plan);
+  cudaError_t e = get_plan(robot, scene, &plan, true, nullptr);
+  if (e == cudaSuccess) {
+    if (plan->ready) e = cudaEventSynchronize(plan->ready);  // the explicit call may wait
+    release_plan(scene, plan);
+  }
   return finish(e, "acro_scene_prepare");
 }
 
@@ -668,6 +687,23 @@ int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double*
   return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream), false,
                               near_mask, margin),
                 "acro_fk_cc_f64");
+}
+
+int64_t acro_fk_cc_workspace_bytes(int64_t n) { return n > 0 ? (int64_t)filter_scratch_bytes(n) : 0; }
+
+int acro_fk_cc_f64_ws(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
+                      int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = check_batch(robot, q, mask, n)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
+  if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
+  if (workspace && workspace_bytes < acro_fk_cc_workspace_bytes(n))
+    return fail(ACRO_E_INVALID, "workspace smaller than acro_fk_cc_workspace_bytes(n)");
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 7u))
+    return fail(ACRO_E_INVALID, "workspace must be 8-byte aligned");
+  return finish(run_fk_cc_f64(robot, scene, q, n, q_layout, mask, as_stream(stream), false,
+                              near_mask, margin, workspace, (size_t)(workspace ? workspace_bytes : 0)),
+                "acro_fk_cc_f64_ws");
 }
 
 int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
@@ -723,7 +759,11 @@ struct HostPipe {
     chunk = 0;
   }
 };
-HostPipe g_pipe;
+// One pipeline per CUDA device (streams and staging buffers belong to a device): calls on
+// different devices run concurrently from different host threads; calls on the same device
+// share its copy engines anyway and take turns.
+constexpr int kMaxPipeDevices = 64;
+HostPipe g_pipes[kMaxPipeDevices];
 }  // namespace
 
 int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
@@ -735,10 +775,12 @@ int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const do
   chunk = (chunk + 31) / 32 * 32;  // chunk boundaries fall on mask words
   if (chunk > n) chunk = (n + 31) / 32 * 32;
   const int ndof = robot->d64.ndof;
-  std::lock_guard<std::mutex> lock(g_pipe.mu);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxPipeDevices) return fail(ACRO_E_UNSUPPORTED, "device ordinal too large");
+  HostPipe& g_pipe = g_pipes[dev];
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
   if (g_pipe.device != dev || g_pipe.chunk < chunk || g_pipe.ndof < ndof) {
     g_pipe.release();
     for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
@@ -796,6 +838,21 @@ static int check_kuka(const AcroRobot* robot) {
   if (!robot) return fail(ACRO_E_INVALID, "robot handle is NULL");
   if (robot->d64.ndof != 6 || robot->d64.prismatic_mask != 0)
     return fail(ACRO_E_UNSUPPORTED, "Kuka IK needs a 6-dof all-revolute chain");
+  // the closed form (robot_examples.py:188-218) is that of the Kuka's DH pattern
+  // (robot_examples.py:161-168): alpha = (pi/2, 0, pi/2, -pi/2, pi/2, 0), a = (a1, a2, 0, 0, 0, 0),
+  // d = (0, 0, 0, d4, 0, d6), no theta offsets.  Any other 6R chain must not get these formulas.
+  const AcroRobotDesc& d = robot->desc;
+  const double sa[6] = {1, 0, 1, -1, 1, 0}, ca[6] = {0, 1, 0, 0, 0, 1};
+  bool ok = true;
+  for (int i = 0; i < 6; ++i) {
+    ok = ok && std::fabs(d.sin_alpha[i] - sa[i]) < 1e-12 && std::fabs(d.cos_alpha[i] - ca[i]) < 1e-12;
+    ok = ok && d.theta[i] == 0.0;
+    if (i >= 2) ok = ok && d.a[i] == 0.0;
+    if (i != 3 && i != 5) ok = ok && d.d[i] == 0.0;
+  }
+  if (!ok)
+    return fail(ACRO_E_UNSUPPORTED,
+                "closed-form IK is only defined for the Kuka DH pattern (robot_examples.py:161-168)");
   return 0;
 }
 
@@ -843,6 +900,9 @@ int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene,
   if (n_points < 0 || samples_per_point < 1) return fail(ACRO_E_INVALID, "bad point / sample count");
   if (!offsets || capacity < 0 || (capacity > 0 && !q_free))
     return fail(ACRO_E_INVALID, "offsets / q_free is NULL");
+  // the compaction moves rows of 6 doubles as three 16-byte pieces
+  if ((reinterpret_cast<uintptr_t>(q_all) | reinterpret_cast<uintptr_t>(q_free)) & 15u)
+    return fail(ACRO_E_INVALID, "q_all and q_free must be 16-byte aligned");
   const int64_t n = n_points * samples_per_point;
   if (int rc = acro_ik_kuka_cc_f64(robot, scene, T, n, q_all, valid, free_mask, stream)) return rc;
   cudaStream_t st = as_stream(stream);
@@ -917,7 +977,7 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
                   "acro_path_cc_f64");
   static const AcroScene empty_scene{};
   const CullPlan* plan = nullptr;
-  cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan);
+  cudaError_t e = get_plan(robot, scene ? scene : &empty_scene, &plan, true, st);
   if (e != cudaSuccess) return finish(e, "acro_path_cc_f64");
   PlanPin pin;
   pin.scene = scene ? scene : &empty_scene;

@@ -94,6 +94,11 @@ struct GridView {
   int32_t skip_nan;   // rows holding NaN are absent IK branches: not evaluated, verdict bit 0
 };
 
+// bounding radii of the robot's radius classes (kernel parameter of the grid builder)
+struct GridClassRadii {
+  double r[kMaxBoxes];
+};
+
 // ---------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------

@@ -11,7 +11,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kFThreads = 128;
 constexpr int kItemCap = 64;      // candidate pairs per warp and round
 #ifndef ACRO_FILTER_MIN_CTAS
-#define ACRO_FILTER_MIN_CTAS 5
+#define ACRO_FILTER_MIN_CTAS 6
 #endif
 #ifndef ACRO_FILTER_DYNAMIC
 #define ACRO_FILTER_DYNAMIC 1

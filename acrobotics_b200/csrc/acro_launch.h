@@ -31,7 +31,7 @@ cudaError_t launch_fk_cc_wave(const RobotDev<double>& rb, const CullTable& ct,
 // production K2 (FP32 filter + candidate grid + exact FP64 fix-up pass); fk_cc_filt.cu
 cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, int dim,
                               int n_classes, const double* origin, double cell,
-                              const double* class_radius_dev, double pad, cudaStream_t st);
+                              const double* class_radius_host, double pad, cudaStream_t st);
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
                                 const GridView& grid, int mask_bits, SceneView<float> sc32,
                                 SceneView<double> sc64, const double* q, int64_t n, int layout,

@@ -312,7 +312,7 @@ template <typename MaskT>
 __global__ void __launch_bounds__(256)
     build_grid_kernel(const SceneView<double> sc, MaskT* __restrict__ cells, int dim,
                       int n_classes, double ox, double oy, double oz, double cell,
-                      const double* __restrict__ class_radius, double pad) {
+                      const GridClassRadii class_radius, double pad) {
   const int64_t per = (int64_t)dim * dim * dim;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= per * n_classes) return;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256)
   const int64_t r = gid - cls * per;
   const int ix = (int)(r % dim), iy = (int)((r / dim) % dim), iz = (int)(r / ((int64_t)dim * dim));
   const double px = ox + (ix + 0.5) * cell, py = oy + (iy + 0.5) * cell, pz = oz + (iz + 0.5) * cell;
-  const double reach = class_radius[cls] + pad;
+  const double reach = class_radius.r[cls] + pad;
   MaskT m = 0;
   for (int j = 0; j < sc.n; ++j) {
     const double* b = sc.boxes + (size_t)j * kSceneStride;
@@ -338,17 +338,19 @@ __global__ void __launch_bounds__(256)
 
 cudaError_t launch_build_grid(SceneView<double> sc, void* cells, int mask_bits, int dim,
                               int n_classes, const double* origin, double cell,
-                              const double* class_radius_dev, double pad, cudaStream_t st) {
+                              const double* class_radius_host, double pad, cudaStream_t st) {
+  GridClassRadii radii;
+  for (int c = 0; c < kMaxBoxes; ++c) radii.r[c] = c < n_classes ? class_radius_host[c] : 0.0;
   const int64_t total = (int64_t)dim * dim * dim * n_classes;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (mask_bits == 32)
     build_grid_kernel<uint32_t><<<blocks, 256, 0, st>>>(sc, (uint32_t*)cells, dim, n_classes,
                                                        origin[0], origin[1], origin[2], cell,
-                                                       class_radius_dev, pad);
+                                                       radii, pad);
   else
     build_grid_kernel<uint64_t><<<blocks, 256, 0, st>>>(sc, (uint64_t*)cells, dim, n_classes,
                                                        origin[0], origin[1], origin[2], cell,
-                                                       class_radius_dev, pad);
+                                                       radii, pad);
   count_launch();
   return cudaGetLastError();
 }

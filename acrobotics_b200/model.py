@@ -111,15 +111,19 @@ class RobotKinematics:
         pass
 
     def _signature(self):
-        """Cheap fingerprint of everything ``_describe`` reads: the descriptor (a ~5 KB ctypes
-        struct) is only rebuilt when it changes.  Transforms are compared by value, so in-place
-        edits of ``tf_base`` / shape transforms are seen; DH tables and box sizes are assumed
-        immutable after construction (the reference never mutates them either)."""
+        """Fingerprint of everything ``_describe`` reads: the descriptor (a ~5 KB ctypes
+        struct) is only rebuilt when it changes.  Everything is compared by value - base and
+        tool-tip transforms, the DH rows and joint types of every link - so in-place edits and
+        swapped links are seen."""
         tip = self.tf_tool_tip
         return (
             np.asarray(self.tf_base, dtype=np.float64).tobytes(),
             None if tip is None else np.asarray(tip, dtype=np.float64).tobytes(),
-            len(self.links),
+            tuple(
+                (float(l.dh.a), float(l.dh.alpha), float(l.dh.d), float(l.dh.theta),
+                 getattr(l.joint_type, "value", l.joint_type))
+                for l in self.links
+            ),
         )
 
     def _handle(self, **kw):
@@ -284,7 +288,12 @@ class Robot(RobotKinematics):
         def scene_sig(sc):
             if sc is None:
                 return None
-            return (len(sc.s), b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in sc.tf_s))
+            # shapes by value (type + extents), transforms by value
+            shapes = tuple(
+                (type(sh).__name__,) + tuple(float(v) for v in getattr(sh, "half_extents", ()))
+                for sh in sc.s
+            )
+            return (shapes, b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in sc.tf_s))
 
         return super()._signature() + (
             bool(self.do_check_self_collision),
@@ -359,9 +368,13 @@ class Robot(RobotKinematics):
         robot_h = self._handle(force_self=_force_self)
         scene_h = scene.native_handle() if scene is not None else None
         if dtype == "f64":
-            rc = lib.acro_fk_cc_f64(
+            # caller-owned scratch: with it the native hot call allocates nothing
+            ws_bytes = int(lib.acro_fk_cc_workspace_bytes(n))
+            ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.int64, device="cuda") if ws_bytes else None
+            rc = lib.acro_fk_cc_f64_ws(
                 robot_h, scene_h, qd.data_ptr(), n, _native.Q_AOS, words.data_ptr(),
                 near.data_ptr() if near is not None else None, float(margin),
+                ws.data_ptr() if ws is not None else None, ws_bytes if ws is not None else 0,
                 device.current_stream_ptr(),
             )
         else:

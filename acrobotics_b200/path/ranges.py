@@ -50,3 +50,23 @@ class SymmetricTolerance(Tolerance):
 
     def __init__(self, dist: float, num_samples: int):
         super().__init__(-dist, dist, num_samples)
+
+
+class QuaternionTolerance(Tolerance):
+    """Ball of orientations: quaternion distance at most ``dist`` (tolerance.py:43-55)."""
+
+    __slots__ = ("dist",)
+
+    def __init__(self, quat_distance: float):
+        self.dist = quat_distance
+        self.lower = self.upper = self.num_samples = None
+        self.has_tolerance = True
+
+    def discretize(self):
+        raise NotImplementedError  # "Future work" in the reference as well
+
+    def reduce_tolerance(self, reduction_factor: float, reference_value: float) -> None:
+        self.dist = self.dist / reduction_factor
+
+    def __repr__(self):
+        return f"QuaternionTolerance({self.dist})"

@@ -1,2 +1,2 @@
 """Module path of the reference (``acrobotics.path.tolerance``); see ``ranges.py``."""
-from .ranges import NoTolerance, SymmetricTolerance, Tolerance  # noqa: F401
+from .ranges import NoTolerance, QuaternionTolerance, SymmetricTolerance, Tolerance  # noqa: F401

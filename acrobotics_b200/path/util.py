@@ -34,3 +34,28 @@ def rpy_to_rot_mat(rxyz):
     R[..., 2, 1] = sx * cz + cx * sy * sz
     R[..., 2, 2] = cx * cy
     return R
+
+
+def rotation_matrix_to_rpy(R):
+    """(..., 3, 3) -> (..., 3): inverse of ``rpy_to_rot_mat`` (R = Rx Ry Rz), the angles the
+    reference's ``fk_rpy`` extracts (``src/acrobotics/robot.py:71-80``, including its
+    ``r_z = atan2(-R01, R22)`` - exact whenever r_x = 0, which is the case the reference's
+    tests cover, ``tests/test_path.py:139-176``).  ``acrolib.geometry.rotation_matrix_to_rpy``
+    itself is un-vendored: for r_x != 0 the textbook ``atan2(-R01, R00)`` is used."""
+    R = np.asarray(R, dtype=np.float64)
+    r_x = np.arctan2(-R[..., 1, 2], R[..., 2, 2])
+    r_y = np.arctan2(R[..., 0, 2], np.sqrt(R[..., 0, 0] ** 2 + R[..., 0, 1] ** 2))
+    r_z = np.arctan2(-R[..., 0, 1], R[..., 0, 0])
+    return np.stack([r_x, r_y, r_z], axis=-1)
+
+
+def is_in_range(x, lower, upper):
+    return not (x > upper or x < lower)
+
+
+def check_rxyz_input(rxyz):
+    """reference path/util.py:11-20"""
+    if np.allclose(abs(rxyz[1]), np.pi / 2):
+        return False
+    return (is_in_range(rxyz[0], -np.pi, np.pi) and is_in_range(rxyz[1], -np.pi / 2, np.pi / 2)
+            and is_in_range(rxyz[2], -np.pi, np.pi))

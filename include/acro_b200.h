@@ -119,11 +119,14 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out);
 void acro_scene_destroy(AcroScene* scene);
 /* Optional: build now what acro_fk_cc_f64 would otherwise build on its first LARGE call
  * (>= 65536 configurations) with this (robot, scene) pair - the candidate grid of the
- * filtered kernel (about 20 MB of device memory owned by the scene handle, ~1 ms, one
- * synchronisation; a scene keeps the eight most recently used grids).  With a grid in
- * place, batches of 4096 configurations and more take the filtered kernel and the hot call
+ * filtered kernel (about 20 MB of device memory owned by the scene handle, ~1 ms; a scene
+ * keeps the eight most recently used grids).  This call waits for the build; a first-use
+ * build inside a hot call is ordered on the caller's stream instead (one cudaMalloc, no
+ * device-wide synchronisation; other streams wait on an event).  With a grid in place,
+ * batches of 4096 configurations and more take the filtered kernel and the hot call
  * allocates nothing but stream-ordered scratch (cudaMallocAsync) for one bit per
- * configuration; without one, smaller batches run the all-FP64 kernel.               */
+ * configuration - or nothing at all through acro_fk_cc_f64_ws; without a grid, smaller
+ * batches run the all-FP64 kernel.                                                    */
 int acro_scene_prepare(const AcroScene* scene, const AcroRobot* robot);
 
 /* ---- the fcl.collide seam -------------------------------------------------------
@@ -156,12 +159,22 @@ int acro_fk_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t 
 int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
                    void* stream);
+/* Same with a caller-owned workspace of acro_fk_cc_workspace_bytes(n) bytes of DEVICE memory
+ * (8-byte aligned; contents undefined on entry and exit): with it, and with the (robot, scene)
+ * pair prepared by acro_scene_prepare, the hot call allocates nothing and synchronises nothing.
+ * workspace may be NULL (then this is acro_fk_cc_f64).                                      */
+int64_t acro_fk_cc_workspace_bytes(int64_t n);
+int acro_fk_cc_f64_ws(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
+                      int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 /* FP32 joint values.  Small batches run an all-FP32 kernel (poses good to ~1e-5); large AoS
  * batches are widened exactly and take the FP64-exact filtered path, i.e. the verdicts are
  * those of acro_fk_cc_f64 at the float-valued joint angles.                              */
 int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, void* stream);
-/* Same, HOST buffers: pipelined H2D/kernel/D2H inside the call.                 */
+/* Same, HOST buffers: pipelined H2D/kernel/D2H inside the call.  The pipeline (three staging
+ * slots, three streams) is per CUDA device: calls on different devices run concurrently from
+ * different host threads, calls on one device take turns.                       */
 int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
                         int64_t n, uint32_t* mask_host, int64_t chunk);
 
@@ -176,7 +189,10 @@ int acro_jac_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t
 /* ---- K5: analytical IK ---------------------------------------------------------
  * Kuka.ik (robot_examples.py:188-218 = arm_2.py:5-104 + spherical_wrist.py:5-30).
  * T (N,4,4) row-major -> q_out (N,8,6), slot = 2*arm_branch + wrist_branch in the
- * reference's order; valid[i] bit s = slot s exists (invalid slots are NaN).    */
+ * reference's order; valid[i] bit s = slot s exists (invalid slots are NaN).
+ * The robot must have the Kuka's DH pattern (robot_examples.py:161-168: alpha =
+ * (pi/2, 0, pi/2, -pi/2, pi/2, 0), a = (a1, a2, 0, 0, 0, 0), d = (0, 0, 0, d4, 0, d6), no
+ * theta offsets); any other chain is refused with ACRO_E_UNSUPPORTED.                */
 int acro_ik_kuka_f64(const AcroRobot* robot, const double* T, int64_t n, double* q_out,
                      uint8_t* valid, void* stream);
 /* arm_2.ik: p (N,3) -> q_out (N,4,3), valid bits [pos_a,pos_b,neg_a,neg_b].      */
@@ -203,7 +219,8 @@ int acro_ik_kuka_cc_f64(const AcroRobot* robot, const AcroScene* scene, const do
  * rows of 6 doubles; rows offsets[p] .. offsets[p+1]-1 belong to point p, in the reference's
  * order (samples in order, each pose's solutions in Kuka.ik's order); offsets has
  * n_points + 1 entries and offsets[n_points] is the total number of surviving solutions
- * (rows beyond `capacity` are not written - compare the total with the capacity).      */
+ * (rows beyond `capacity` are not written - compare the total with the capacity).
+ * q_all and q_free must be 16-byte aligned (rows are moved as 16-byte pieces).           */
 int acro_joint_solutions_csr_f64(const AcroRobot* robot, const AcroScene* scene, const double* T,
                                  int64_t n_points, int32_t samples_per_point, double* q_all,
                                  uint8_t* valid, uint8_t* free_mask, double* q_free,
