@@ -198,26 +198,41 @@ struct FilterCtx {
   float* s_saved;        // n_saved * 12 * 32 floats (this warp)
   const float* s_half;   // kMaxSaved * 4 floats (CTA wide)
   uint16_t* list;        // kItemCap entries (this warp)
+  unsigned char* extra;  // the caller's own per-warp bytes (start of this warp's block)
   int n_scene;
 };
 
-// shared memory the filter needs per CTA of `warps` warps (after the caller's own data)
-inline size_t filter_ctx_bytes(int warps, int n_scene, int n_saved) {
-  return sizeof(float) * n_scene * kSceneStrideF + sizeof(float) * warps * n_saved * 12 * 32 +
-         sizeof(float) * kMaxSaved * 4 + sizeof(uint16_t) * warps * kItemCap;
+// Shared-memory layout: [saved-slot half extents: kMaxSaved * 4 floats][scene: n_scene * 16
+// floats][one block per warp: `extra` caller bytes, the candidate list, the saved poses].
+// Everything a warp touches besides the CTA-wide tables sits at a fixed offset from ONE base
+// address, which keeps the address arithmetic (and its rematerialisation under register
+// pressure) out of the inner loops.
+__host__ __device__ inline size_t filter_warp_block_bytes(int n_saved, size_t extra) {
+  return extra + sizeof(uint16_t) * kItemCap + sizeof(float) * n_saved * 12 * 32;
 }
 
-// carve the per-warp context out of `base` (4-byte aligned), CTA of `warps` warps
+// shared memory the filter needs per CTA of `warps` warps (`extra`: caller bytes per warp,
+// a multiple of 16)
+inline size_t filter_ctx_bytes(int warps, int n_scene, int n_saved, size_t extra = 0) {
+  return sizeof(float) * kMaxSaved * 4 + sizeof(float) * n_scene * kSceneStrideF +
+         warps * filter_warp_block_bytes(n_saved, extra);
+}
+
+// carve the per-warp context out of `base` (16-byte aligned), CTA of `warps` warps
 __device__ __forceinline__ FilterCtx filter_ctx_carve(unsigned char* base, int warps, int warp,
-                                                      int n_scene, int n_saved) {
+                                                      int n_scene, int n_saved, size_t extra = 0) {
   FilterCtx c;
-  float* s_scene = reinterpret_cast<float*>(base);
-  c.s_scene = s_scene;
-  c.s_saved = s_scene + n_scene * kSceneStrideF + warp * n_saved * 12 * 32;
-  float* s_half = s_scene + n_scene * kSceneStrideF + warps * n_saved * 12 * 32;
+  float* s_half = reinterpret_cast<float*>(base);
+  float* s_scene = s_half + kMaxSaved * 4;
+  unsigned char* wb = reinterpret_cast<unsigned char*>(s_scene + n_scene * kSceneStrideF) +
+                      warp * filter_warp_block_bytes(n_saved, extra);
   c.s_half = s_half;
-  c.list = reinterpret_cast<uint16_t*>(s_half + kMaxSaved * 4) + warp * kItemCap;
+  c.s_scene = s_scene;
+  c.extra = wb;
+  c.list = reinterpret_cast<uint16_t*>(wb + extra);
+  c.s_saved = reinterpret_cast<float*>(wb + extra + sizeof(uint16_t) * kItemCap);
   c.n_scene = n_scene;
+  (void)warps;
   return c;
 }
 
@@ -225,8 +240,10 @@ __device__ __forceinline__ FilterCtx filter_ctx_carve(unsigned char* base, int w
 __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
                                                  const RobotDev<float>& rb,
                                                  const SceneView<float>& sc, int n_saved) {
-  float* s_scene = reinterpret_cast<float*>(base);
-  float* s_half = s_scene + sc.n * kSceneStrideF + warps * n_saved * 12 * 32;
+  float* s_half = reinterpret_cast<float*>(base);
+  float* s_scene = s_half + kMaxSaved * 4;
+  (void)warps;
+  (void)n_saved;
   for (int k = threadIdx.x; k < sc.n * kSceneStrideF; k += blockDim.x) {
     const int j = k >> 4, e = k & 15;
     s_scene[k] = sc.boxes[j * kSceneStride + kScenePerm[e]];

@@ -83,14 +83,13 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   const unsigned lane = t & 31;
   const int warp = t >> 5;
   constexpr int kWarps = kFThreads / 32;
-  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * 2 * 32 * NDOF;
-  long long* s_stash =
-      reinterpret_cast<long long*>(reinterpret_cast<double*>(smem_raw) + kWarps * 2 * 32 * NDOF) +
-      warp * 64;
-  unsigned char* ctx_base = smem_raw + sizeof(double) * kWarps * 2 * 32 * NDOF +
-                            sizeof(long long) * kWarps * 64;
-  filter_ctx_stage(ctx_base, kWarps, rb, sc, n_saved);
-  const FilterCtx ctx = filter_ctx_carve(ctx_base, kWarps, warp, sc.n, n_saved);
+  // this warp's own bytes inside its block of the filter context: the two joint-row buffers,
+  // then the stash
+  constexpr size_t kExtra = sizeof(double) * 2 * 32 * NDOF + sizeof(long long) * 64;
+  filter_ctx_stage(smem_raw, kWarps, rb, sc, n_saved);
+  const FilterCtx ctx = filter_ctx_carve(smem_raw, kWarps, warp, sc.n, n_saved, kExtra);
+  double* s_q = reinterpret_cast<double*>(ctx.extra);
+  long long* s_stash = reinterpret_cast<long long*>(ctx.extra + sizeof(double) * 2 * 32 * NDOF);
   __syncthreads();
 
   const int64_t n_chunks = (n + 31) >> 5;
@@ -365,8 +364,8 @@ size_t filter_scratch_bytes(int64_t n) {
 
 size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
   const int warps = kFThreads / 32;
-  return sizeof(double) * warps * 2 * 32 * ndof + sizeof(long long) * warps * 64 +
-         filter_ctx_bytes(warps, n_scene, n_saved);
+  return filter_ctx_bytes(warps, n_scene, n_saved,
+                          sizeof(double) * 2 * 32 * ndof + sizeof(long long) * 64);
 }
 
 // resident CTAs of the persistent filter kernel on the current device
