@@ -12,6 +12,10 @@
 // One launch per layer transition (a min-plus product V' = min_j (V_j + c(j, k))): a warp owns
 // one target node, its lanes stride over the source nodes staged through shared memory, then
 // an arg-min reduction across the warp.  FP64 throughout.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
 #include "acro_launch.h"
 
 namespace acro {
@@ -189,7 +193,8 @@ __global__ void dp_init_kernel(const double* __restrict__ state_cost, int64_t n0
 __global__ void dp_backtrack_kernel(const double* __restrict__ value,
                                     const int32_t* __restrict__ pred,
                                     const int64_t* __restrict__ offsets, int64_t n_layers,
-                                    int64_t* __restrict__ path_rows, double* __restrict__ length) {
+                                    int64_t* __restrict__ path_rows, double* __restrict__ length,
+                                    const unsigned* __restrict__ sync) {
   const int lane = threadIdx.x;
   const int64_t lo = offsets[n_layers - 1], hi = offsets[n_layers];
   double best = 1.0 / 0.0;
@@ -209,7 +214,8 @@ __global__ void dp_backtrack_kernel(const double* __restrict__ value,
     }
   }
   if (lane == 0) {
-    *length = best;
+    // a grid barrier of the persistent kernel gave up: the values are not trustworthy
+    *length = (sync && sync[1] != 0u) ? __longlong_as_double(0x7ff8000000000000LL) : best;
     int64_t node = best_k;
     for (int64_t layer = n_layers - 1; layer >= 0; --layer) {
       path_rows[layer] = node;
@@ -219,6 +225,264 @@ __global__ void dp_backtrack_kernel(const double* __restrict__ value,
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// Whole graph in ONE launch (the common planner case: thousands of layers of a few hundred to
+// a couple of thousand nodes).  A layer transition is ~0.5 us of FP64 work for the whole chip,
+// but the layers depend on each other, so with one launch per layer the chain is bound by the
+// kernel boundary (~9 us per layer measured).  Here one persistent CTA per SM (cooperative
+// launch: all CTAs are co-resident) walks the layers; target node k of a layer belongs to warp
+// k / G of CTA k % G, so a layer spreads over every SM's FP64 pipe.
+//
+// Synchronisation is by DATA FLOW, not by a grid barrier (a counter barrier over 148 CTAs was
+// measured at ~2.5 us per layer): the value array is pre-filled with a NaN sentinel, a consumer
+// spins on the very values it needs (ld.volatile from L2) until they are no longer NaN, and a
+// producer simply stores its value (st.cg).  Nothing else produced during the walk is read
+// during the walk (the joint rows are input, `pred` is only read by the back-tracking kernel),
+// so no fences are needed; a CTA can run at most one layer ahead of the slowest one.  The next
+// layer's joint rows (independent of the values) are copied into shared memory with cp.async
+// while the current layer is evaluated.  A spin that does not complete within ~2 s sets a
+// sticky flag, after which nobody waits any more - the kernel can not hang the device; the
+// back-tracking kernel then reports a NaN length.
+// ---------------------------------------------------------------------------
+constexpr int kDpPThreads = 256;
+constexpr int kDpPWarps = kDpPThreads / 32;
+constexpr int kDpPMaxNodes = 1920;  // two padded row buffers of 6-dof layers fit in 227 KB
+#ifndef ACRO_DP_UNROLL
+#define ACRO_DP_UNROLL 8
+#endif
+constexpr int kDpPUnroll = ACRO_DP_UNROLL;
+#ifndef ACRO_DP_TIMING
+#define ACRO_DP_TIMING 0
+#endif
+#ifndef ACRO_DP_FENCE
+#define ACRO_DP_FENCE 0
+#endif
+
+__device__ __forceinline__ void dp_cp_async_16(void* smem_dst, const void* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void dp_cp_async_8(void* smem_dst, const void* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ double dp_ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// value of a source node, waiting for its producer if necessary
+__device__ __forceinline__ double dp_wait_value(const double* p, unsigned* flag) {
+  double v = dp_ld_volatile(p);
+  if (v == v) return v;
+  long long t0 = 0;
+  for (unsigned spins = 1;; ++spins) {
+    v = dp_ld_volatile(p);
+    if (v == v) return v;
+    if ((spins & 1023u) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      if (*reinterpret_cast<volatile unsigned*>(flag) != 0u) return v;
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s
+        atomicExch(flag, 1u);
+        return v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool dp_better(double ob, int oj, double b, int bj) {
+  return ob < b || (ob == b && oj >= 0 && (bj < 0 || oj < bj));
+}
+
+// One persistent CTA per SM; in every layer target node k belongs to warp k / G of CTA k % G
+// (a layer of ~840 nodes is one target per warp on ~6 warps of every SM).
+template <int COST, int NDOF>
+__global__ void __launch_bounds__(kDpPThreads, 1)
+    dp_persistent_kernel(const double* __restrict__ q, const int64_t* __restrict__ offsets,
+                         const int64_t n_layers, const double* __restrict__ state_cost,
+                         double* value, int32_t* __restrict__ pred, const DpWeights w,
+                         unsigned* sync) {
+  extern __shared__ __align__(16) unsigned char dp_smem[];
+  // rows padded to an odd number of doubles: lane j reads row j without bank conflicts (the
+  // evaluation is bound by these shared-memory reads: with a pitch of 6 doubles - 2-way
+  // conflicts - a layer takes 6200 cycles instead of 4800)
+  constexpr int kPitch = NDOF | 1;
+  constexpr int kRowCap = kDpPMaxNodes * kPitch;     // doubles per row buffer
+  double* s_q = reinterpret_cast<double*>(dp_smem);  // [2][kRowCap]
+  double* s_v = s_q + 2 * kRowCap;                   // [kDpPMaxNodes]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  unsigned* flag = sync + 1;
+  // asynchronous copy of a layer's joint rows into buffer `buf`
+  auto prefetch_rows = [&](int64_t layer, int buf) {
+    const int64_t r0 = __ldg(offsets + layer);
+    const int cnt = (int)(__ldg(offsets + layer + 1) - r0) * NDOF;  // doubles
+    const double* src = q + r0 * NDOF;
+    double* dst = s_q + buf * kRowCap;
+    for (int e = tid; e < cnt; e += kDpPThreads) {
+      const int r = e / NDOF, c = e - r * NDOF;
+      dp_cp_async_8(dst + r * kPitch + c, src + e);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  // the joint rows are read once, i.e. from DRAM: pull them into L2 two layers ahead
+  auto prefetch_l2 = [&](int64_t layer) {
+    if (layer >= n_layers) return;
+    const int64_t r0 = __ldg(offsets + layer);
+    const int64_t bytes = (__ldg(offsets + layer + 1) - r0) * NDOF * (int64_t)sizeof(double);
+    const char* src = reinterpret_cast<const char*>(q + r0 * NDOF);
+    for (int64_t b = (int64_t)tid * 128; b < bytes; b += (int64_t)kDpPThreads * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
+  };
+  prefetch_l2(1);
+  prefetch_l2(2);
+  prefetch_rows(0, 0);
+  {
+    const int64_t n0 = __ldg(offsets + 1) - __ldg(offsets);
+    for (int64_t i = (int64_t)blockIdx.x * kDpPThreads + tid; i < n0; i += (int64_t)G * kDpPThreads) {
+      pred[i] = -1;
+      __stcg(value + i, state_cost ? state_cost[i] : 0.0);
+    }
+  }
+#if ACRO_DP_TIMING
+  long long t_pre = 0, t_wait = 0, t_comp = 0, t_tail = 0, tt;
+#define ACRO_DP_T(acc) { const long long now = clock64(); acc += now - tt; tt = now; }
+  tt = clock64();
+#else
+#define ACRO_DP_T(acc)
+#endif
+  for (int64_t l = 1; l < n_layers; ++l) {
+    const int64_t s0 = __ldg(offsets + l - 1), d0 = __ldg(offsets + l);
+    const int ns = (int)(d0 - s0), nd = (int)(__ldg(offsets + l + 1) - d0);
+    const double* sq = s_q + ((l - 1) & 1) * kRowCap;
+    // this layer's rows are the source rows of the next transition: start copying them now
+    if (l + 1 < n_layers) prefetch_rows(l, l & 1);
+    prefetch_l2(l + 2);
+    // this warp's first target row (read-only input): in flight while the values arrive
+    const int k_first = blockIdx.x + G * warp;
+    double tq0[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) tq0[i] = k_first < nd ? __ldg(q + (d0 + k_first) * NDOF + i) : 0.0;
+    ACRO_DP_T(t_pre)
+    for (int j = tid; j < ns; j += kDpPThreads) s_v[j] = dp_wait_value(value + s0 + j, flag);
+    if (l + 1 < n_layers)
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    ACRO_DP_T(t_wait)
+    for (int k = k_first; k < nd; k += G * kDpPWarps) {
+      double tq[NDOF];
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) tq[i] = k == k_first ? tq0[i] : __ldg(q + (d0 + k) * NDOF + i);
+      double best = 1.0 / 0.0;
+      int best_j = -1;
+      // kDpPUnroll independent source nodes per lane and step (the FP64 accumulation of one
+      // edge is a dependent chain - its order is part of the result - so the parallelism has to
+      // come from several edges in flight); ascending index within a lane and a strict
+      // comparison: the lowest index wins ties, like the per-layer kernels
+      for (int j0 = lane; j0 < ns; j0 += 32 * kDpPUnroll) {
+        double c2[kDpPUnroll];
+#pragma unroll
+        for (int u = 0; u < kDpPUnroll; ++u) {
+          const int j = j0 + 32 * u;
+          const bool ok = j < ns;
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i) {
+            const double d = (ok ? sq[j * kPitch + i] : tq[i]) - tq[i];
+            if (COST == 0) acc += fabs(d);
+            if (COST == 1 || COST == 2) acc = fma(d, d, acc);
+            if (COST == 3) acc = fma(w.w[i] * d, d, acc);
+          }
+          if (COST == 1) acc = sqrt(acc);
+          c2[u] = ok ? s_v[j] + acc : 1.0 / 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kDpPUnroll; ++u)
+          if (c2[u] < best) {
+            best = c2[u];
+            best_j = j0 + 32 * u;
+          }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+        if (dp_better(ob, oj, best, best_j)) {
+          best = ob;
+          best_j = oj;
+        }
+      }
+      if (lane == 0) {
+        pred[d0 + k] = best_j;
+        __stcg(value + d0 + k, best + (state_cost ? state_cost[d0 + k] : 0.0));
+#if ACRO_DP_FENCE
+        __threadfence();
+#endif
+      }
+    }
+    ACRO_DP_T(t_comp)
+    __syncthreads();  // s_v and the row buffer of this transition are free again
+    ACRO_DP_T(t_tail)
+  }
+#if ACRO_DP_TIMING
+  if ((blockIdx.x == 0 || blockIdx.x == 100) && (tid == 0 || tid == 224))
+    printf("cta %d thr %d cycles/layer: pre %lld wait %lld comp %lld tail %lld\n", blockIdx.x, tid,
+           t_pre / n_layers, t_wait / n_layers, t_comp / n_layers, t_tail / n_layers);
+#endif
+}
+
+// launches the persistent kernel when the graph is eligible (*launched), else leaves the
+// per-layer path to the caller
+static cudaError_t try_persistent(const double* q, int ndof, const int64_t* offsets_host,
+                                  const int64_t* offsets_dev, int64_t n_layers, int cost_type,
+                                  const DpWeights& w, const double* state_cost, double* value,
+                                  int32_t* pred, unsigned* sync, cudaStream_t st, bool* launched) {
+  *launched = false;
+  static const bool disabled = std::getenv("ACRO_DP_PERSISTENT") &&
+                               std::string(std::getenv("ACRO_DP_PERSISTENT")) == "0";
+  if (disabled || n_layers < 32) return cudaSuccess;
+  for (int64_t l = 0; l < n_layers; ++l)
+    if (offsets_host[l + 1] - offsets_host[l] > kDpPMaxNodes) return cudaSuccess;
+  // two row buffers + the source values
+  const size_t smem = sizeof(double) * ((size_t)2 * kDpPMaxNodes * (ndof | 1) + kDpPMaxNodes);
+  int dev = 0, sms = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || sms < 1 || smem > 227 * 1024) return cudaSuccess;
+  const void* fn = nullptr;
+#define ACRO_DP_PICK(C)                                                       \
+  ACRO_DISPATCH_NDOF(ndof, { fn = (const void*)dp_persistent_kernel<C, NDOF>; })
+  switch (cost_type) {
+    case 0: ACRO_DP_PICK(0); break;
+    case 1: ACRO_DP_PICK(1); break;
+    case 2: ACRO_DP_PICK(2); break;
+    default: ACRO_DP_PICK(3); break;
+  }
+#undef ACRO_DP_PICK
+  int per_sm = 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDpPThreads, smem);
+  if (e != cudaSuccess || per_sm < 1) return e;
+  // NaN sentinel in every value: "not produced yet"
+  const int64_t total = offsets_host[n_layers];
+  e = cudaMemsetAsync(value, 0xFF, sizeof(double) * (size_t)total, st);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&q,     (void*)&offsets_dev, (void*)&n_layers, (void*)&state_cost,
+                  (void*)&value, (void*)&pred,        (void*)&w,        (void*)&sync};
+  e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)sms), dim3(kDpPThreads), args, smem, st);
+  if (e == cudaSuccess) {
+    count_launch();
+    *launched = true;
+  }
+  return e;
 }
 
 cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offsets_host,
@@ -231,10 +495,25 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  bool persistent = false;
+  unsigned* sync = nullptr;  // [0] barrier counter, [1] sticky "a barrier timed out" flag
+  {
+    cudaError_t ep = cudaMallocAsync(&sync, 2 * sizeof(unsigned), st);
+    if (ep == cudaSuccess) ep = cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned), st);
+    if (ep == cudaSuccess)
+      ep = try_persistent(q, ndof, offsets_host, offsets_dev, n_layers, cost_type, w, state_cost,
+                          value, pred, sync, st, &persistent);
+    if (ep != cudaSuccess) {
+      if (sync) cudaFreeAsync(sync, st);
+      return ep;
+    }
+  }
   const int64_t n0 = offsets_host[1] - offsets_host[0];
-  dp_init_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(state_cost, n0, value, pred);
-  count_launch();
-  for (int64_t l = 1; l < n_layers; ++l) {
+  if (!persistent) {
+    dp_init_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(state_cost, n0, value, pred);
+    count_launch();
+  }
+  for (int64_t l = 1; l < n_layers && !persistent; ++l) {
     const int64_t s0 = offsets_host[l - 1], d0 = offsets_host[l];
     const int64_t ns = d0 - s0, nd = offsets_host[l + 1] - d0;
     if (ns > 0x7fffffff || nd > 0x7fffffff) return cudaErrorInvalidValue;
@@ -265,9 +544,11 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
 #undef ACRO_DP_LAUNCH
     count_launch();
   }
-  dp_backtrack_kernel<<<1, 32, 0, st>>>(value, pred, offsets_dev, n_layers, path_rows, length);
+  dp_backtrack_kernel<<<1, 32, 0, st>>>(value, pred, offsets_dev, n_layers, path_rows, length, sync);
   count_launch();
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  const cudaError_t e2 = cudaFreeAsync(sync, st);
+  return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace acro

@@ -17,6 +17,9 @@
 #ifndef ACRO_JAC_POS_CTAS
 #define ACRO_JAC_POS_CTAS 5
 #endif
+#ifndef ACRO_IK_CTAS
+#define ACRO_IK_CTAS 4
+#endif
 #ifndef ACRO_JAC_RPY_CTAS
 #define ACRO_JAC_RPY_CTAS 4
 #endif
@@ -248,9 +251,13 @@ __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, doub
 }
 
 // Kuka.ik for one pose (robot_examples.py:188-218).  T: 16 doubles row-major.
-// sol[slot][6], returns the validity bit set (slot = 2*arm + wrist).
+// emit(k, pair) receives the two solutions of arm branch k (slots 2k and 2k+1, 12 doubles; NaN
+// when the branch does not exist) as soon as they are known - the caller parks them in shared
+// memory instead of keeping all 48 values in registers.  Returns the validity bit set
+// (slot = 2*arm + wrist).
+template <typename Emit>
 __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const double* Tin,
-                                            double sol[8][6]) {
+                                            Emit emit) {
   Tf<double> Tw;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -319,21 +326,19 @@ __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const do
       tf_mul_dh<double>(F, (k & 1) ? S.s3[br] : -S.s3[br], S.c3[br], half_pi_cos, 1.0, d4, 0.0);
       double w1[3], w2[3];
       wrist_ik(F.r, Tw.r, w1, w2);
-      sol[2 * k][0] = q1; sol[2 * k][1] = q2; sol[2 * k][2] = q3;
-      sol[2 * k][3] = w1[0]; sol[2 * k][4] = w1[1]; sol[2 * k][5] = w1[2];
-      sol[2 * k + 1][0] = q1; sol[2 * k + 1][1] = q2; sol[2 * k + 1][2] = q3;
-      sol[2 * k + 1][3] = w2[0]; sol[2 * k + 1][4] = w2[1]; sol[2 * k + 1][5] = w2[2];
+      emit(k, make_double2(q1, q2), make_double2(q3, w1[0]), make_double2(w1[1], w1[2]),
+           make_double2(q1, q2), make_double2(q3, w2[0]), make_double2(w2[1], w2[2]));
       valid |= 3u << (2 * k);
     } else {
-#pragma unroll
-      for (int e = 0; e < 6; ++e) sol[2 * k][e] = sol[2 * k + 1][e] = nan;
+      const double2 nn = make_double2(nan, nan);
+      emit(k, nn, nn, nn, nn, nn, nn);
     }
   }
   return valid;
 }
 
 template <bool WITH_CC>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, WITH_CC ? 1 : ACRO_IK_CTAS)
     ik_kuka_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
                    const double* __restrict__ T, int64_t n, double* __restrict__ q_out,
                    uint8_t* __restrict__ valid, uint8_t* __restrict__ free_mask, bool vec_in,
@@ -353,9 +358,27 @@ __global__ void __launch_bounds__(kTile)
 #pragma unroll
     for (int k = 0; k < 16; ++k) Tin[k] = (k % 5 == 0) ? 1.0 : 0.0;
   }
-  alignas(16) double sol[8][6];
-  const unsigned vbits = kuka_ik(rb, Tin, sol);
-  stage_store_rows<double, 48>(smem_raw, &sol[0][0], q_out, row0, n, 48, 0, vec_out);
+  // every arm branch's pair of solutions goes straight into this thread's row of the staging
+  // tile (row of 48 doubles = 24 16-byte units, odd unit stride: conflict free)
+  using RS = RowStage<double, 48>;
+  int4* s_tile = reinterpret_cast<int4*>(smem_raw);
+  double2* s_tile2 = reinterpret_cast<double2*>(smem_raw);
+  double* s_plain = reinterpret_cast<double*>(smem_raw);
+  const int t = threadIdx.x;
+  const unsigned vbits = kuka_ik(rb, Tin, [&](int k, double2 u0, double2 u1, double2 u2, double2 u3,
+                                              double2 u4, double2 u5) {
+    const double2 u[6] = {u0, u1, u2, u3, u4, u5};
+    if (vec_out) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) s_tile2[t * RS::STRIDE + 6 * k + e] = u[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        s_plain[t * 49 + 12 * k + 2 * e] = u[e].x;
+        s_plain[t * 49 + 12 * k + 2 * e + 1] = u[e].y;
+      }
+    }
+  });
   if (idx < n) valid[idx] = (uint8_t)vbits;
   if (WITH_CC) {
     unsigned freebits = 0;
@@ -363,12 +386,32 @@ __global__ void __launch_bounds__(kTile)
       const bool act = idx < n && ((vbits >> sl) & 1);
       double qv[6];
 #pragma unroll
-      for (int e = 0; e < 6; ++e) qv[e] = act ? sol[sl][e] : 0.0;
+      for (int e = 0; e < 6; ++e)
+        qv[e] = !act ? 0.0
+                     : (vec_out ? reinterpret_cast<const double*>(s_tile + t * RS::STRIDE)[6 * sl + e]
+                                : s_plain[t * 49 + 6 * sl + e]);
       Verdict<double, false> v;
       config_collision<double, 6, false>(rb, qv, s_scene, sc.n, 0.0, act, v);
       if (act && !v.hit) freebits |= 1u << sl;
     }
     if (idx < n) free_mask[idx] = (uint8_t)freebits;
+  }
+  // flat copy-out of the tile: whole 128-byte lines
+  __syncthreads();
+  const int64_t left = n - row0;
+  const int rows = left < kTile ? (int)left : kTile;
+  if (vec_out) {
+    const int total = rows * RS::UNITS;
+    for (int e = t; e < total; e += kTile) {
+      const int r = e / RS::UNITS, c = e - r * RS::UNITS;
+      __stcs(reinterpret_cast<int4*>(q_out + (row0 + r) * 48) + c, s_tile[r * RS::STRIDE + c]);
+    }
+  } else {
+    const int total = rows * 48;
+    for (int e = t; e < total; e += kTile) {
+      const int r = e / 48, c = e - r * 48;
+      __stcs(q_out + (row0 + r) * 48 + c, s_plain[r * 49 + c]);
+    }
   }
 }
 

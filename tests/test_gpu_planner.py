@@ -213,3 +213,25 @@ def test_planner_demo_end_to_end(gpu):
     ref = dp_oracle.shortest_path([q_free[off[i]:off[i + 1]] for i in range(len(path))], "sum_squared")
     assert abs(ref["length"] - length) <= 1e-9 * max(1.0, length)
     assert np.array_equal(np.array(ref["path"]), q_path)
+
+
+@pytest.mark.parametrize("cost", ["norm_l1", "norm_l2", "sum_squared", "weighted_sum_squared"])
+def test_shortest_path_many_layers_single_launch(gpu, cost):
+    """Graphs of >= 32 small layers take the persistent single-launch kernel (grid barrier
+    between layers): same path, same length as the CPU DP, ties included."""
+    from acrobotics_b200 import _native
+    from acrobotics_b200.planning import shortest_path
+    from oracle import dp_oracle
+
+    rng = np.random.default_rng(12)
+    sizes = list(rng.integers(1, 400, 150)) + [1, 1500, 2, 1920, 1]
+    layers = [np.round(rng.uniform(-3, 3, (n, 6)), 1) for n in sizes]  # rounding creates ties
+    w = np.array([1.0, 2.0, 0.5, 0.1, 3.0, 1.5]) if cost == "weighted_sum_squared" else None
+    sc = [rng.uniform(0, 2, n) for n in sizes]
+    for state_cost in (None, sc):
+        ref = dp_oracle.shortest_path(layers, cost, w, state_cost)
+        before = _native.launch_count()
+        got = shortest_path(layers, cost, w, state_cost)
+        assert _native.launch_count() - before == 2  # the persistent kernel + the backtrack
+        assert got["success"] and abs(got["length"] - ref["length"]) <= 1e-9 * max(1, ref["length"])
+        assert np.array_equal(np.array(got["path"]), np.array(ref["path"]))
