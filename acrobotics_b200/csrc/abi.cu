@@ -52,6 +52,8 @@ struct AcroScene {
   float* dev32;
   CullTable cull;  // FP32 face-axis cull table (kernel parameter of the wavefront K2)
   double bound;    // max over boxes of |centre| + bounding radius
+  double max_centre;    // max over boxes of |centre|
+  double max_half_sum;  // max over boxes of half[0] + half[1] + half[2]
   // plans are created on first use (or by acro_scene_prepare), never freed before the scene
   mutable std::mutex mu;
   mutable std::vector<CullPlan*> plans;
@@ -276,6 +278,90 @@ struct PlanPin {  // RAII holder
   ~PlanPin() { release_plan(scene, plan); }
 };
 
+// ---------------------------------------------------------------------------
+// FP32 filter tolerance: a running error bound, not a heuristic.
+//
+// delta must bound |s_fp32 - s_fp64| for every quantity s that FCL's test compares with zero,
+// for every configuration the filter accepts (revolute |q| <= 1e8, prismatic |q| <= q_lin_max),
+// every robot box and every partner box (scene boxes; other robot boxes for self pairs).  The
+// FP64 side is treated as exact (its own rounding, ~1e-15, is covered by the final slack).
+// u = 2^-24 (FP32 unit roundoff; an FMA rounds once).  Norms: Frobenius for the 3x3 rotation
+// error (it bounds every entry and every column), Euclidean for position errors.
+//
+//  sin/cos   |s32 - sin q| <= e_t = 1.4e-7: sincos_filter reduces q in FP64 (error <= 1.2e-8
+//            at |q| = 1e8), rounds the reduced angle to FP32 and evaluates the Cephes
+//            polynomials; measured over 8e7 arguments: 6.4e-8 (sin), 9.5e-8 (cos)
+//            (tests/test_filter_tolerance_cpu.py repeats the measurement).
+//  joint k   R_k = R_{k-1} D_k.  ||dD||_F <= 2 e_t + 2u (the four trigonometric entries of D
+//            times cos/sin(alpha), cos^2 + sin^2 = 1; + the FP32 constants).  The factored
+//            evaluation tf_mul_dh rounds each output column to within 2u, 4u, 4u (column
+//            norms <= 1): 6u in Frobenius norm.  Rotations are isometries, so
+//            rho_k <= rho_{k-1} (1 + ||dD||) + ||dD|| + 6u.
+//            p_k = p_{k-1} + a u_k + d z_{k-1}:
+//            pi_k <= pi_{k-1} + |a| (rho_k + u) + |d| (rho_{k-1} + u) + 2u |p_k|
+//            (+ u |q| for a prismatic joint, whose travel is rounded to FP32).
+//  box       offset = pure translation t: R_box = R_k, c = p + R t:
+//            pi_b <= pi_k + |t| (rho_k + u) + 3u (|p| + |t|); general offset: one more product,
+//            rho_b <= rho_k (1 + 3u) + 3u + 9u.
+//  pair      p = T2 - c1, D >= |p|.  eps_p = pi_1 + pi_2 + u D.  Entries of R = R1^T R2:
+//            eps_R = rho_1 + rho_2 + 3u.  Projections R^T p: eps_pp = max(rho) D + eps_p + 3u D.
+//            face axis  |t| - (sum |R| A + B):  eps_pp + eps_R S + 5u (S + D)
+//            edge axis  |pp R - pp R| - (A Q + A Q + B Q + B Q), |R| <= 1:
+//                       2 (D eps_R + eps_pp) + 2u D + eps_R S + 6u S
+//            with S = the largest sum of half extents entering one radius.
+// A scene box has rho_2 = 3u, pi_2 = sqrt(3) u |T2| (its FP32 copy).  The bound is evaluated
+// with D = the largest possible centre distance, i.e. it holds for every pair, near or far.
+// ---------------------------------------------------------------------------
+double derive_filter_tolerance(const AcroRobot* robot, const AcroScene* scene) {
+  const double u = std::ldexp(1.0, -24), e_t = 1.4e-7;
+  const AcroRobotDesc& d = robot->desc;
+  const int n = d.ndof;
+  auto norm3 = [](double x, double y, double z) { return std::sqrt(x * x + y * y + z * z); };
+  double rho = 3.0 * u;  // tf_base rounded to FP32
+  double pnorm = norm3(d.tf_base[3], d.tf_base[7], d.tf_base[11]);
+  double pi_ = std::sqrt(3.0) * u * pnorm;
+  double rho_box = 0.0, pi_box = 0.0, reach_box = 0.0, half_sum = 0.0;
+  auto visit_boxes = [&](int carrier) {
+    for (int b = 0; b < d.n_boxes; ++b) {
+      if (d.boxes[b].carrier != carrier) continue;
+      const double* t = d.boxes[b].tf;
+      const double tn = norm3(t[3], t[7], t[11]);
+      const bool ident = is_identity_rot(t);
+      const double rb = ident ? rho : rho * (1.0 + 3.0 * u) + 12.0 * u;
+      const double pb = pi_ + tn * (rho + u) + 3.0 * u * (pnorm + tn);
+      rho_box = std::max(rho_box, rb);
+      pi_box = std::max(pi_box, pb);
+      reach_box = std::max(reach_box, pnorm + tn);
+      half_sum = std::max(half_sum, d.boxes[b].half[0] + d.boxes[b].half[1] + d.boxes[b].half[2]);
+    }
+  };
+  visit_boxes(ACRO_CARRIER_BASE);
+  const double dD = 2.0 * e_t + 2.0 * u;
+  for (int k = 0; k < n; ++k) {
+    const double rho_prev = rho;
+    rho = rho_prev * (1.0 + dD) + dD + 6.0 * u;
+    const double a = std::fabs(d.a[k]);
+    const double len = d.joint_type[k] ? robot->q_lin_max : std::fabs(d.d[k]);
+    pnorm += a + len;
+    pi_ += a * (rho + u) + len * (rho_prev + u) + 2.0 * u * pnorm + (d.joint_type[k] ? u * len : 0.0);
+    visit_boxes(k);
+    if (k == n - 1) visit_boxes(ACRO_CARRIER_TOOL);
+  }
+  // partner: scene box or (self pairs) another robot box
+  const double sc_centre = scene ? scene->max_centre : 0.0;
+  const double sc_half = scene ? scene->max_half_sum : 0.0;
+  const double rho2 = std::max(3.0 * u, robot->desc.n_self_pairs > 0 ? rho_box : 0.0);
+  const double pi2 = std::max(std::sqrt(3.0) * u * sc_centre, robot->desc.n_self_pairs > 0 ? pi_box : 0.0);
+  const double D = reach_box + std::max(sc_centre, reach_box);
+  const double S = half_sum + std::max(sc_half, half_sum);
+  const double eps_p = pi_box + pi2 + u * D;
+  const double eps_R = rho_box + rho2 + 3.0 * u;
+  const double eps_pp = std::max(rho_box, rho2) * D + eps_p + 3.0 * u * D;
+  const double face = eps_pp + eps_R * S + 5.0 * u * (S + D);
+  const double edge = 2.0 * (D * eps_R + eps_pp) + 2.0 * u * D + eps_R * S + 6.0 * u * S;
+  return 1.05 * std::max(face, edge) + 1.0e-9;
+}
+
 // create = false: only look an existing plan up (*out stays nullptr when there is none)
 // A new plan is built on stream `st` (no device-wide synchronisation); every consumer makes its
 // stream wait on the plan's `ready` event, so a plan found by another thread / stream while its
@@ -332,15 +418,10 @@ cudaError_t get_plan(const AcroRobot* robot, const AcroScene* scene, const CullP
   p->mask_bits = scene->n <= 32 ? 32 : 64;
   p->cells = nullptr;
   p->ready = nullptr;
-  // FP32 filter tolerance.  Every SAT quantity is the result of O(100) FP32 operations on
-  // numbers bounded by the workspace size P (unit roundoff 6e-8, sin/cos good to 1.2e-7, six
-  // chained links): a first-order worst case is ~6e-6 P.  Measured over 4 M configurations x
-  // 96 pairs x 15 axes (acro_measure_filter_error, tests/test_gpu_k2_variants.py):
-  // 1.5e-6 for P = 4.5.  delta = 2e-5 P is 3x the crude bound and ~60x the measurement.
-  const double base_norm = std::sqrt(p->centre[0] * p->centre[0] + p->centre[1] * p->centre[1] +
-                                     p->centre[2] * p->centre[2]);
-  const double P = base_norm + robot->reach + scene->bound;
-  const double delta = 2.0e-5 * std::max(1.0, P);
+  // FP32 filter tolerance: the running error bound of derive_filter_tolerance (measured over
+  // 4 M configurations x 96 pairs x 15 axes with acro_measure_filter_error: 1.5e-6 for the
+  // Kuka and the 16-box scene, for which the bound is ~1.1e-4)
+  const double delta = derive_filter_tolerance(robot, scene);
   const double half = std::max(robot->reach, 1e-3);
   const double cell = 2.0 * half / p->dim;
   const double origin[3] = {p->centre[0] - half, p->centre[1] - half, p->centre[2] - half};
@@ -582,7 +663,7 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
   *out = nullptr;
   if (n > ACRO_MAX_SCENE_BOXES) return fail(ACRO_E_UNSUPPORTED, "too many scene boxes");
   std::vector<double> p64((size_t)(n > 0 ? n : 1) * kSceneStride, 0.0);
-  double bound = 0.0;
+  double bound = 0.0, max_centre = 0.0, max_half_sum = 0.0;
   for (int j = 0; j < n; ++j) {
     double* o = &p64[(size_t)j * kSceneStride];
     double r2 = 0, hmax = 0;
@@ -595,13 +676,18 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out) {
     }
     o[15] = std::sqrt(r2) * (1.0 + 1e-6);
     o[16] = hmax;
-    bound = std::max(bound, std::sqrt(o[9] * o[9] + o[10] * o[10] + o[11] * o[11]) + o[15]);
+    const double cn = std::sqrt(o[9] * o[9] + o[10] * o[10] + o[11] * o[11]);
+    bound = std::max(bound, cn + o[15]);
+    max_centre = std::max(max_centre, cn);
+    max_half_sum = std::max(max_half_sum, o[12] + o[13] + o[14]);
   }
   std::vector<float> p32(p64.size());
   for (size_t k = 0; k < p64.size(); ++k) p32[k] = (float)p64[k];
   AcroScene* s = new AcroScene;
   s->n = n;
   s->bound = bound;
+  s->max_centre = max_centre;
+  s->max_half_sum = max_half_sum;
   s->device = 0;
   s->dev64 = nullptr;
   s->dev32 = nullptr;

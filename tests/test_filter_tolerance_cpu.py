@@ -1,0 +1,57 @@
+"""The one constant of the FP32 filter's error bound that is not arithmetic: the accuracy of its
+sin/cos (acrobotics_b200/csrc/acro_filter.cuh: sincos_filter = FP64 range reduction, FP32
+rounding of the reduced angle, Cephes minimax polynomials on [-pi/4, pi/4]).
+derive_filter_tolerance (csrc/abi.cu) uses e_t = 1.4e-7; this test re-measures the error of the
+same operation sequence (FMA emulated exactly in double precision) over 8 M arguments."""
+import numpy as np
+
+f32 = np.float32
+
+
+def _fma(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+
+def _mul(a, b):
+    return (a.astype(np.float64) * b.astype(np.float64)).astype(f32)
+
+
+def test_filter_sincos_error_is_below_the_bound_constant():
+    rng = np.random.default_rng(0)
+    worst_s = worst_c = 0.0
+    for _ in range(4):
+        r = rng.uniform(-np.pi / 4 * (1 + 1e-7), np.pi / 4 * (1 + 1e-7), 2_000_000)  # reduced angle (FP64)
+        x = r.astype(f32)
+        z = _mul(x, x)
+        c = lambda v: np.full_like(x, v, dtype=f32)  # noqa: E731
+        sp = _fma(_fma(c(-1.9515295891e-4), z, c(8.3321608736e-3)), z, c(-1.6666654611e-1))
+        sp = _fma(_mul(sp, z), x, x)
+        cp = _fma(_fma(c(2.443315711809948e-5), z, c(-1.388731625493765e-3)), z, c(4.166664568298827e-2))
+        cp = _fma(_mul(cp, z), z, _fma(c(-0.5), z, c(1.0)))
+        worst_s = max(worst_s, float(np.abs(sp.astype(np.float64) - np.sin(r)).max()))
+        worst_c = max(worst_c, float(np.abs(cp.astype(np.float64) - np.cos(r)).max()))
+    print(f"[filter-bound] sincos_filter: max |sin error| {worst_s:.3e}, max |cos error| {worst_c:.3e}; "
+          "bound constant e_t = 1.4e-7")
+    assert worst_s < 1.2e-7 and worst_c < 1.2e-7
+
+
+def test_range_reduction_in_fp64_is_exact_enough():
+    """q - k pi/2 with the two-term constant of sincos_filter: error far below e_t up to |q| = 1e8."""
+    from fractions import Fraction
+
+    def fma(a, b, c):  # exact product and sum, one rounding (int / int division rounds correctly)
+        v = Fraction(a) * Fraction(b) + Fraction(c)
+        return v.numerator / v.denominator
+
+    hi, lo = 1.57079632679489655800e+00, 6.12323399573676603587e-17
+    rng = np.random.default_rng(1)
+    qs = np.concatenate([rng.uniform(-1e8, 1e8, 3000), rng.uniform(-10, 10, 3000)])
+    # pi/2 to 60 digits
+    half_pi = Fraction("1.57079632679489661923132169163975144209858469968755291048747")
+    worst = 0.0
+    for q in qs:
+        k = int(np.rint(q * 0.63661977236758134308))
+        r = fma(-float(k), lo, fma(-float(k), hi, float(q)))
+        exact = Fraction(float(q)) - k * half_pi
+        worst = max(worst, abs(float(Fraction(r) - exact)))
+    assert worst < 1e-9

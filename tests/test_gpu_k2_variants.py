@@ -175,6 +175,88 @@ def test_filter_tolerance_covers_measured_fp32_error(gpu):
         assert worst_p < delta.value / 10
 
 
+def _measure(robot, scene, q):
+    import ctypes
+
+    import torch
+
+    lib = _native.load()
+    qd = torch.from_numpy(np.ascontiguousarray(q)).cuda()
+    out = torch.zeros(2, dtype=torch.float64, device="cuda")
+    delta = ctypes.c_double()
+    _native.check(lib.acro_filter_tolerance(robot._handle(), scene.native_handle(), ctypes.byref(delta)))
+    _native.check(lib.acro_measure_filter_error(robot._handle(), scene.native_handle(), qd.data_ptr(),
+                                                qd.shape[0], out.data_ptr(), None))
+    worst_s, worst_p = out.cpu().tolist()
+    return delta.value, worst_s, worst_p
+
+
+def test_filter_tolerance_is_a_bound_at_the_worst_corners(gpu):
+    """The tolerance is a derived running error bound (abi.cu: derive_filter_tolerance), so it
+    must hold - with room - where FP32 is worst: an 8-joint chain with 2 m links, a base 50 m
+    from the origin, 1 mm plates, scene boxes whose edges are parallel to the robot's to within
+    1e-7 rad, prismatic travel at its limits, joint angles of 1e6 rad.  For each case: measured
+    max |s_fp32 - s_fp64| over all link-box x scene-box pairs x 15 axes < delta, and the
+    filtered verdicts equal the all-FP64 kernel's."""
+    rng = np.random.default_rng(77)
+    cases = []
+    # (1) eight revolute joints, a and d up to 2 m
+    links = []
+    for i in range(8):
+        dh = ab.DHLink(float(rng.uniform(0.5, 2.0)), float(rng.choice([0, np.pi / 2, -np.pi / 2, 0.7])),
+                       float(rng.uniform(0.0, 2.0)), 0.0)
+        links.append(ab.Link(dh, ab.JointType.revolute,
+                             ab.Scene([ab.Box(*rng.uniform(0.2, 1.5, 3))], [translation(*rng.uniform(-0.5, 0.5, 3))])))
+    long_arm = ab.Robot(links)
+    big_scene = scene16(seed=9, n_boxes=32)
+    for t in big_scene.tf_s:
+        t[:3, 3] *= 6.0
+    cases.append(("8 dof, 2 m links", long_arm, big_scene, rng.uniform(-np.pi, np.pi, (400_000, 8))))
+    # (2) base 50 m from the origin, scene moved along
+    far = ab.Kuka()
+    shift = np.array([30.0, -38.0, 12.0])  # |shift| = 49.9
+    far.tf_base = translation(*shift)
+    far_scene = scene16()
+    for t in far_scene.tf_s:
+        t[:3, 3] += shift
+    cases.append(("base at 50 m", far, far_scene, random_configs(400_000, 6, seed=1)))
+    # (3) 1 mm plates: in the scene and on the robot
+    thin = ab.Kuka()
+    thin.links[2].geometry.s[0] = ab.Box(0.4, 0.3, 0.001)
+    plates = ab.Scene([ab.Box(2, 2, 0.001), ab.Box(0.001, 1.0, 1.0), ab.Box(0.6, 0.001, 0.8)],
+                      [translation(0, 0, -0.2), translation(0.7, 0, 0.5), translation(0, -0.6, 0.6)])
+    cases.append(("1 mm plates", thin, plates, random_configs(400_000, 6, seed=2)))
+    # (4) near-parallel edges: scene boxes in link frames of sampled configurations, turned by
+    #     1e-7 rad, and configurations around those samples
+    k = ab.Kuka()
+    q0 = random_configs(12, 6, seed=3)
+    frames = k.fk_batch(q0, all_links=True)
+    tfs = []
+    for i in range(12):
+        tf = frames[i, i % 6].copy()
+        a = 1e-7
+        tf[:3, :3] = tf[:3, :3] @ np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        tf[:3, 3] += tf[:3, :3] @ np.array([0.05, 0.25, 0.0])
+        tfs.append(tf)
+    par_scene = ab.Scene([ab.Box(0.3, 0.3, 0.3)] * 12, tfs)
+    qn = np.repeat(q0, 30_000, axis=0) + rng.normal(0, 1e-3, (360_000, 6))
+    cases.append(("near-parallel edges", k, par_scene, qn))
+    # (5) prismatic travel at +-q_lin_max (4 m) and beyond (those go to the FP64 pass)
+    rail = ab.KukaOnRail()
+    qr = random_configs(300_000, 7, seed=4)
+    qr[:, 0] = rng.choice([-4.0, 4.0, -3.999, 3.999, 4.5, -7.0], len(qr))
+    cases.append(("rail at its limits", rail, scene16(), qr))
+    # (6) huge joint angles (revolute |q| up to 1e6)
+    cases.append(("|q| ~ 1e6", ab.Kuka(), scene16(), random_configs(300_000, 6, seed=5) * 3e5))
+    for name, robot, scene, q in cases:
+        qm = q if name != "rail at its limits" else q[np.abs(q[:, 0]) <= 4.0]
+        delta, worst_s, worst_p = _measure(robot, scene, qm)
+        print(f"[filter-bound] {name:22s} delta {delta:.3e}  max|s32-s64| {worst_s:.3e}  "
+              f"(head-room {delta / max(worst_s, 1e-30):5.1f}x)  centre error {worst_p:.3e}")
+        assert 0 < worst_s < delta and worst_p < delta, name
+        _all_variants_agree(robot, q, scene)
+
+
 def test_margin_mode_through_the_filter(gpu):
     """return_near=True: verdicts and the +-1e-6 m bucket from the filtered kernel (filter run
     with tolerance delta + margin, FP64 margin evaluation of the flagged configurations) equal
