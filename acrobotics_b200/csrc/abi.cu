@@ -256,7 +256,7 @@ int grid_dim_setting() {
   int d = g_grid_dim.load(std::memory_order_relaxed);
   if (d < 0) {
     const char* e = std::getenv("ACRO_K2_GRID");
-    d = e ? std::atoi(e) : 96;
+    d = e ? std::atoi(e) : 128;
     d = d < 8 ? 8 : (d > 160 ? 160 : d);
     g_grid_dim.store(d);
   }

@@ -105,7 +105,7 @@ int acro_device_count(void);
  *                  without a near mask; all variants return identical verdicts;
  *   "k2_split"   = "auto" (default) | 0 | k: slot after which the filtered kernel regroups the
  *                  still undecided configurations into full warps (0 = single pass);
- *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 96).
+ *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 128).
  * The environment variables ACRO_K2_VARIANT / ACRO_K2_SPLIT / ACRO_K2_GRID set the initial values.    */
 int acro_set_option(const char* name, const char* value);
 
@@ -119,7 +119,7 @@ int acro_scene_create(const AcroBox* boxes, int32_t n, AcroScene** out);
 void acro_scene_destroy(AcroScene* scene);
 /* Optional: build now what acro_fk_cc_f64 would otherwise build on its first LARGE call
  * (>= 65536 configurations) with this (robot, scene) pair - the candidate grid of the
- * filtered kernel (about 20 MB of device memory owned by the scene handle, ~1 ms; a scene
+ * filtered kernel (about 50 MB of device memory owned by the scene handle for six radius classes, ~1 ms; a scene
  * keeps the eight most recently used grids).  This call waits for the build; a first-use
  * build inside a hot call is ordered on the caller's stream instead (one cudaMalloc, no
  * device-wide synchronisation; other streams wait on an event).  With a grid in place,
