@@ -16,6 +16,9 @@ constexpr int kItemCap = 64;      // candidate pairs per warp and round
 #ifndef ACRO_FILTER_DYNAMIC
 #define ACRO_FILTER_DYNAMIC 1
 #endif
+#ifndef ACRO_FILTER_PIN_IDS
+#define ACRO_FILTER_PIN_IDS 1
+#endif
 #ifndef ACRO_SAT_PRETEST
 #define ACRO_SAT_PRETEST 0
 #endif

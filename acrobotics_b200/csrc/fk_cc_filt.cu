@@ -73,23 +73,56 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
                         const unsigned early_mask, const double* __restrict__ q, const int64_t n, const int layout,
                         uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask,
                         unsigned long long* __restrict__ work_counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [q buffers: 4 warps x 2 x 32*NDOF doubles (prefetch double buffer; pass 2 borrows the idle one)]
-  // [stash: 4 warps x 64 int64][filter context]
-  // Kuka x 16 boxes: 34 KB per CTA.  (Keeping the joint rows of the stashed configurations in
-  // shared memory instead of re-reading them from L2 in pass 2 drops residency by one CTA per
-  // SM and was measured 9 % slower.)
+  // Shared memory.  Everything whose size is known at compile time is a STATIC array, so that its
+  // address is an immediate plus the warp / lane offset: with one dynamic block carved by hand
+  // the compiler, short of registers at six CTAs per SM, rematerialised the base pointers 19
+  // times per chunk (S2R + 8 uniform instructions each: 8 % of all issued instructions).  Only
+  // the saved poses of the self-collision partners (n_saved is a property of the robot) stay
+  // dynamic.  Kuka x 16 boxes: 35 KB per CTA.  (Keeping the joint rows of the stashed
+  // configurations in shared memory instead of re-reading them from L2 in pass 2 drops
+  // residency by one CTA per SM and was measured 9 % slower.)
+  constexpr int kWarps = kFThreads / 32;
+  constexpr int kSceneCap = sizeof(MaskT) == 4 ? 32 : kMaxScene;  // a 32-bit mask means <= 32 boxes
+  __shared__ __align__(16) double s_q_all[kWarps][2 * 32 * NDOF];  // prefetch double buffer per warp
+  __shared__ long long s_stash_all[kWarps][64];
+  __shared__ __align__(16) float s_scene_st[kSceneCap * kSceneStrideF];
+  __shared__ float s_half_st[kMaxSaved * 4];
+  __shared__ uint16_t s_list_all[kWarps][kItemCap];
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // [kWarps][n_saved][12 * 32] floats
   const int t = threadIdx.x;
+#if ACRO_FILTER_PIN_IDS
+  // opaque to the optimiser: keeps the lane / warp index in a register instead of re-reading
+  // SR_TID and re-deriving every shared-memory address from it inside the loops
+  unsigned lane = t & 31;
+  int warp = t >> 5;
+  asm volatile("" : "+r"(lane));
+  asm volatile("" : "+r"(warp));
+#else
   const unsigned lane = t & 31;
   const int warp = t >> 5;
-  constexpr int kWarps = kFThreads / 32;
-  // this warp's own bytes inside its block of the filter context: the two joint-row buffers,
-  // then the stash
-  constexpr size_t kExtra = sizeof(double) * 2 * 32 * NDOF + sizeof(long long) * 64;
-  filter_ctx_stage(smem_raw, kWarps, rb, sc, n_saved);
-  const FilterCtx ctx = filter_ctx_carve(smem_raw, kWarps, warp, sc.n, n_saved, kExtra);
-  double* s_q = reinterpret_cast<double*>(ctx.extra);
-  long long* s_stash = reinterpret_cast<long long*>(ctx.extra + sizeof(double) * 2 * 32 * NDOF);
+#endif
+  for (int k = t; k < sc.n * kSceneStrideF; k += kFThreads) {
+    const int j = k >> 4, e = k & 15;
+    s_scene_st[k] = sc.boxes[j * kSceneStride + kScenePerm[e]];
+  }
+  for (int b = t; b < rb.n_boxes; b += kFThreads) {
+    const int sl = rb.boxes[b].save_slot;
+    if (sl >= 0) {
+      s_half_st[4 * sl + 0] = rb.boxes[b].half[0];
+      s_half_st[4 * sl + 1] = rb.boxes[b].half[1];
+      s_half_st[4 * sl + 2] = rb.boxes[b].half[2];
+      s_half_st[4 * sl + 3] = rb.boxes[b].radius;
+    }
+  }
+  FilterCtx ctx;
+  ctx.s_scene = s_scene_st;
+  ctx.s_half = s_half_st;
+  ctx.list = s_list_all[warp];
+  ctx.s_saved = reinterpret_cast<float*>(smem_raw) + warp * n_saved * 12 * 32;
+  ctx.extra = nullptr;
+  ctx.n_scene = sc.n;
+  double* s_q = s_q_all[warp];
+  long long* s_stash = s_stash_all[warp];
   __syncthreads();
 
   const int64_t n_chunks = (n + 31) >> 5;
@@ -363,9 +396,10 @@ size_t filter_scratch_bytes(int64_t n) {
 }
 
 size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
-  const int warps = kFThreads / 32;
-  return filter_ctx_bytes(warps, n_scene, n_saved,
-                          sizeof(double) * 2 * 32 * ndof + sizeof(long long) * 64);
+  // the dynamic part only: the saved poses of the self-collision partners (the rest is static)
+  (void)ndof;
+  (void)n_scene;
+  return sizeof(float) * (kFThreads / 32) * (size_t)n_saved * 12 * 32;
 }
 
 // resident CTAs of the persistent filter kernel on the current device
@@ -406,7 +440,8 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
   ACRO_DISPATCH_NDOF(rb32.ndof, {
     const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved);
     auto launch = [&](auto kern) -> cudaError_t {
-      if (smem > 48 * 1024) {
+      // static (<= 24 KB) + dynamic shared memory beyond 48 KB needs the opt-in
+      if (smem > 24 * 1024) {
         cudaError_t e2 =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e2 != cudaSuccess) return e2;

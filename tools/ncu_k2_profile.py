@@ -52,12 +52,14 @@ def sass_tally():
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
                          text=True).stdout
     warp, thr = collections.Counter(), collections.Counter()
-    hdr2, use = None, False
+    hdr2, use, taken = None, False, False
     for row in csv.reader(txt.splitlines()):
         if not row:
             continue
         if row[0] == "Kernel Name":
-            use = bool(pat.search(row[1])) and "fixup" not in row[1]
+            # the page may list a launch more than once: tally the first matching block only
+            use = bool(pat.search(row[1])) and "fixup" not in row[1] and not taken
+            taken = taken or use
             hdr2 = None
         elif row[0] == "Address":
             hdr2 = row
