@@ -282,14 +282,14 @@ struct PlanPin {  // RAII holder
 // FP32 filter tolerance: a running error bound, not a heuristic.
 //
 // delta must bound |s_fp32 - s_fp64| for every quantity s that FCL's test compares with zero,
-// for every configuration the filter accepts (revolute |q| <= 1e8, prismatic |q| <= q_lin_max),
+// for every configuration the filter accepts (revolute |q| < 2^26, prismatic |q| <= q_lin_max),
 // every robot box and every partner box (scene boxes; other robot boxes for self pairs).  The
 // FP64 side is treated as exact (its own rounding, ~1e-15, is covered by the final slack).
 // u = 2^-24 (FP32 unit roundoff; an FMA rounds once).  Norms: Frobenius for the 3x3 rotation
 // error (it bounds every entry and every column), Euclidean for position errors.
 //
 //  sin/cos   |s32 - sin q| <= e_t = 1.4e-7: sincos_filter reduces q in FP64 (error <= 1.2e-8
-//            at |q| = 1e8), rounds the reduced angle to FP32 and evaluates the Cephes
+//            at |q| = 2^26), rounds the reduced angle to FP32 and evaluates the Cephes
 //            polynomials; measured over 8e7 arguments: 6.4e-8 (sin), 9.5e-8 (cos)
 //            (tests/test_filter_tolerance_cpu.py repeats the measurement).
 //  joint k   R_k = R_{k-1} D_k.  ||dD||_F <= 2 e_t + 2u (the four trigonometric entries of D

@@ -300,13 +300,21 @@ amb = false;
       const int i = slot - 1;
       double qi = qfn(i);  // lanes without a configuration read an arbitrary (unused) value
       const bool prismatic = PRISM && ((rb.prismatic_mask >> i) & 1);
-      // joint values the FP32 chain cannot follow within its error bound
-      const double lim = prismatic ? (double)grid.q_lin_max : 1.0e8;
-      if (!done && !(fabs(qi) <= lim)) {
-        amb = !(grid.skip_nan && qi != qi);
-        done = true;  // decided by the FP64 pass (or an absent IK branch)
+      // joint values the FP32 chain cannot follow within its error bound: revolute |q| >= 2^26
+      // (6.7e7; one integer compare on the exponent, which also catches NaN and Inf),
+      // prismatic travel beyond the range the bound covers
+      bool out_of_range;
+      if (prismatic)
+        out_of_range = !(fabs(qi) <= (double)grid.q_lin_max);
+      else
+        out_of_range = ((unsigned)__double2hiint(qi) & 0x7fffffffu) >= 0x41900000u;
+      if (out_of_range) {
+        if (!done) {
+          amb = !(grid.skip_nan && qi != qi);
+          done = true;  // decided by the FP64 pass (or an absent IK branch)
+        }
+        qi = 0.0;
       }
-      if (!(fabs(qi) <= lim)) qi = 0.0;
       float s, c;
       if (PRISM) {
         sincos_filter(prismatic ? (double)rb.theta[i] : qi, s, c);
@@ -357,14 +365,16 @@ amb = false;
         if (do_self) {
           for (int k = rb.pair_begin[b]; k < rb.pair_begin[b + 1]; ++k) {
             const int sl = rb.boxes[rb.partner[k]].save_slot;
-            const float* sv = s_saved + sl * 12 * 32 + lane;
+            // saved pose of the partner: 12 floats per lane as three 16-byte pieces (a lane
+            // stride of 48 bytes is conflict free for 16-byte accesses)
+            const float4* sv = reinterpret_cast<const float4*>(s_saved) + (sl * 32 + (int)lane) * 3;
+            const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];  // R0..R3 | R4..R7 | R8, c0, c1, c2
             // partner's face axes against this box's bounding sphere, padded
-            const float d0 = cw[0] - sv[9 * 32], d1 = cw[1] - sv[10 * 32],
-                        d2 = cw[2] - sv[11 * 32];
+            const float d0 = cw[0] - s2.y, d1 = cw[1] - s2.z, d2 = cw[2] - s2.w;
             const float ra = bx.radius + delta;
-            const float y0 = fmaf(sv[6 * 32], d2, fmaf(sv[3 * 32], d1, sv[0] * d0));
-            const float y1 = fmaf(sv[7 * 32], d2, fmaf(sv[4 * 32], d1, sv[1 * 32] * d0));
-            const float y2 = fmaf(sv[8 * 32], d2, fmaf(sv[5 * 32], d1, sv[2 * 32] * d0));
+            const float y0 = fmaf(s1.z, d2, fmaf(s0.w, d1, s0.x * d0));
+            const float y1 = fmaf(s1.w, d2, fmaf(s1.x, d1, s0.y * d0));
+            const float y2 = fmaf(s2.x, d2, fmaf(s1.y, d1, s0.z * d0));
             const bool sep = (fabsf(y0) > s_half[4 * sl + 0] + ra) |
                              (fabsf(y1) > s_half[4 * sl + 1] + ra) |
                              (fabsf(y2) > s_half[4 * sl + 2] + ra);
@@ -390,10 +400,12 @@ amb = false;
           rB = ob[15];
         } else {
           const int sl = other - 64;
-          const float* sv = s_saved + sl * 12 * 32 + owner;
-#pragma unroll
-          for (int e = 0; e < 9; ++e) R2[e] = sv[e * 32];
-          T2[0] = sv[9 * 32]; T2[1] = sv[10 * 32]; T2[2] = sv[11 * 32];
+          const float4* sv = reinterpret_cast<const float4*>(s_saved) + (sl * 32 + owner) * 3;
+          const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];
+          R2[0] = s0.x; R2[1] = s0.y; R2[2] = s0.z; R2[3] = s0.w;
+          R2[4] = s1.x; R2[5] = s1.y; R2[6] = s1.z; R2[7] = s1.w;
+          R2[8] = s2.x;
+          T2[0] = s2.y; T2[1] = s2.z; T2[2] = s2.w;
           B0 = s_half[4 * sl]; B1 = s_half[4 * sl + 1]; B2 = s_half[4 * sl + 2];
           rB = s_half[4 * sl + 3];
         }
@@ -477,11 +489,10 @@ amb = false;
       }
 
       if (do_self && bx.save_slot >= 0) {
-        float* sv = s_saved + bx.save_slot * 12 * 32 + lane;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) sv[e * 32] = Rw[e];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) sv[(9 + e) * 32] = cw[e];
+        float4* sv = reinterpret_cast<float4*>(s_saved) + (bx.save_slot * 32 + (int)lane) * 3;
+        sv[0] = make_float4(Rw[0], Rw[1], Rw[2], Rw[3]);
+        sv[1] = make_float4(Rw[4], Rw[5], Rw[6], Rw[7]);
+        sv[2] = make_float4(Rw[8], cw[0], cw[1], cw[2]);
       }
     }
   }

@@ -253,7 +253,7 @@ int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* m
  * calls expose the evidence: the tolerance used for a (robot, scene) pair, and the measured
  * distance between the FP32 and FP64 decision quantities over a batch of configurations
  * (device pointers; out2[0] = max |s_fp32 - s_fp64| over every configuration x robot box x
- * scene box x axis, out2[1] = max error of a box centre).  Revolute joints within |q| <= 1e8. */
+ * scene box x axis, out2[1] = max error of a box centre).  Revolute joints within |q| < 2^26 (6.7e7). */
 int acro_filter_tolerance(const AcroRobot* robot, const AcroScene* scene, double* delta);
 int acro_measure_filter_error(const AcroRobot* robot, const AcroScene* scene, const double* q,
                               int64_t n, double* out2, void* stream);
