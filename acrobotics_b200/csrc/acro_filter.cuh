@@ -270,7 +270,9 @@ __device__ __forceinline__ void filter_ctx_stage(unsigned char* base, int warps,
 // slot_end < 0 means "to the robot's last slot".  `retired` = the lane needs no further pass
 // (surely colliding, or handed to the FP64 pass / skipped).
 // PRISM = false compiles the prismatic-joint handling out (rb.prismatic_mask must be 0).
-template <int NDOF, typename MaskT, bool PRISM, typename QFn>
+// ROTID = true: every box offset of the robot is a pure translation (the common case: the
+// reference's example robots); the box rotation then IS the link frame's and no copy is made.
+template <int NDOF, typename MaskT, bool PRISM, bool ROTID = false, typename QFn>
 __device__ __forceinline__ void filter_chunk(const RobotDev<float>& rb, const GridView& grid,
                                              const FilterCtx& ctx, const unsigned lane,
                                              const bool active, QFn qfn, bool& hit, bool& amb,
@@ -326,19 +328,34 @@ amb = false;
     }
     for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
       const BoxDev<float>& bx = rb.boxes[b];
-      float Rw[9], cw[3];
-      if (bx.rot_identity) {
+      float Rw_copy[9], cw[3];
+      const float* Rw = ROTID ? T.r : Rw_copy;
+      if (ROTID || bx.rot_identity) {
+        if (!ROTID) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Rw[k] = T.r[k];
+          for (int k = 0; k < 9; ++k) Rw_copy[k] = T.r[k];
+        }
+#if ACRO_F32X2
+        {  // rows 0 and 1 as one packed lane pair (the pairing of tf_mul_dh), row 2 scalar
+          const float2 c01 = fma2(bx.off[11], make_float2(T.r[2], T.r[5]),
+                                  fma2(bx.off[7], make_float2(T.r[1], T.r[4]),
+                                       fma2(bx.off[3], make_float2(T.r[0], T.r[3]),
+                                            make_float2(T.p[0], T.p[1]))));
+          cw[0] = c01.x;
+          cw[1] = c01.y;
+          cw[2] = fmaf(T.r[8], bx.off[11], fmaf(T.r[7], bx.off[7], fmaf(T.r[6], bx.off[3], T.p[2])));
+        }
+#else
 #pragma unroll
         for (int r = 0; r < 3; ++r)
           cw[r] = fmaf(T.r[3 * r + 2], bx.off[11],
                        fmaf(T.r[3 * r + 1], bx.off[7], fmaf(T.r[3 * r], bx.off[3], T.p[r])));
+#endif
       } else {
         Tf<float> W;
         tf_mul<float>(W, T, bx.off);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Rw[k] = W.r[k];
+        for (int k = 0; k < 9; ++k) Rw_copy[k] = W.r[k];
 #pragma unroll
         for (int r = 0; r < 3; ++r) cw[r] = W.p[r];
       }

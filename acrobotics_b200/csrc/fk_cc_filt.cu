@@ -66,7 +66,7 @@ __device__ __forceinline__ void cp_async_wait() {
 //           ever decide a configuration - and everything after split_slot) with full lanes,
 //           and OR late verdicts into the mask words with atomics.
 // split_slot = 0 keeps the single pass (slot windows of filter_chunk).
-template <int NDOF, typename MaskT, bool PRISM>
+template <int NDOF, typename MaskT, bool PRISM, bool ROTID>
 __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved, const int split_slot,
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
     __syncwarp();
 
     bool hit, amb, retired;
-    filter_chunk<NDOF, MaskT, PRISM>(rb, grid, ctx, lane, act, [=](int i) { return qp[i * qs]; },
+    filter_chunk<NDOF, MaskT, PRISM, ROTID>(rb, grid, ctx, lane, act, [=](int i) { return qp[i * qs]; },
                                      hit, amb, retired, check_mask, slot_end);
 
     if (second) {
@@ -453,12 +453,16 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
       return cudaSuccess;
     };
     const bool prism = rb32.prismatic_mask != 0;
+    bool rotid = !prism;  // the specialised instantiation exists for all-revolute chains
+    for (int b = 0; b < rb32.n_boxes; ++b) rotid = rotid && rb32.boxes[b].rot_identity != 0;
     if (mask_bits == 32)
-      e = prism ? launch(fk_cc_filter_kernel<NDOF, uint32_t, true>)
-                : launch(fk_cc_filter_kernel<NDOF, uint32_t, false>);
+      e = prism   ? launch(fk_cc_filter_kernel<NDOF, uint32_t, true, false>)
+          : rotid ? launch(fk_cc_filter_kernel<NDOF, uint32_t, false, true>)
+                  : launch(fk_cc_filter_kernel<NDOF, uint32_t, false, false>);
     else
-      e = prism ? launch(fk_cc_filter_kernel<NDOF, uint64_t, true>)
-                : launch(fk_cc_filter_kernel<NDOF, uint64_t, false>);
+      e = prism   ? launch(fk_cc_filter_kernel<NDOF, uint64_t, true, false>)
+          : rotid ? launch(fk_cc_filter_kernel<NDOF, uint64_t, false, true>)
+                  : launch(fk_cc_filter_kernel<NDOF, uint64_t, false, false>);
     if (e != cudaSuccess) return e;
     count_launch();
     e = cudaGetLastError();
