@@ -37,11 +37,13 @@ enum : int { kSep = 0, kHit = 1, kAmb = 2 };
 // (q - k pi/2, exact to ~1e-16 for |q| < 1e8), the polynomials run in FP32 on
 // [-pi/4, pi/4] (Cephes sinf/cosf minimax coefficients, abs error < 1.2e-7).
 __device__ __forceinline__ void sincos_filter(double q, float& s, float& c) {
-  const double t = q * 0.63661977236758134308;  // 2/pi
-  const int k = __double2int_rn(t);
-  const double kd = (double)k;
-  double r = fma(-kd, 1.57079632679489655800e+00, q);
-  r = fma(-kd, 6.12323399573676603587e-17, r);
+  // k = rint(q * 2/pi) by the magic-number trick (|q| < 2^26: the sum is exact to the unit,
+  // its low word is k in two's complement): two DADDs instead of F2I + I2F.  The second term
+  // of pi/2 (6.1e-17) would change r by |k| 6.1e-17 < 2.7e-9: part of the bound's e_t.
+  const double tm = fma(q, 0.63661977236758134308, 6755399441055744.0);  // 1.5 * 2^52
+  const int k = __double2loint(tm);
+  const double kd = tm - 6755399441055744.0;
+  const double r = fma(-kd, 1.57079632679489655800e+00, q);
   const float x = (float)r;
   const float z = x * x;
   float sp = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
@@ -453,6 +455,7 @@ amb = false;
             }
           }
           __syncwarp();
+          if (b2 == 0u) break;  // nobody had a second candidate: this box is finished
           continue;
         }
         int incl = c;

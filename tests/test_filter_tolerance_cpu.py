@@ -36,22 +36,25 @@ def test_filter_sincos_error_is_below_the_bound_constant():
 
 
 def test_range_reduction_in_fp64_is_exact_enough():
-    """q - k pi/2 with the two-term constant of sincos_filter: error far below e_t up to |q| = 1e8."""
+    """q - k pi/2 as sincos_filter computes it (k by the magic-number trick, one FMA with the
+    FP64 value of pi/2): the error is |k| * 6.1e-17 < 2.7e-9 up to |q| = 2^26, far below e_t."""
     from fractions import Fraction
 
     def fma(a, b, c):  # exact product and sum, one rounding (int / int division rounds correctly)
         v = Fraction(a) * Fraction(b) + Fraction(c)
         return v.numerator / v.denominator
 
-    hi, lo = 1.57079632679489655800e+00, 6.12323399573676603587e-17
+    hi, magic = 1.57079632679489655800e+00, 6755399441055744.0
     rng = np.random.default_rng(1)
-    qs = np.concatenate([rng.uniform(-1e8, 1e8, 3000), rng.uniform(-10, 10, 3000)])
-    # pi/2 to 60 digits
+    qs = np.concatenate([rng.uniform(-2.0 ** 26, 2.0 ** 26, 3000), rng.uniform(-10, 10, 3000)])
     half_pi = Fraction("1.57079632679489661923132169163975144209858469968755291048747")
-    worst = 0.0
+    worst = worst_r = 0.0
     for q in qs:
-        k = int(np.rint(q * 0.63661977236758134308))
-        r = fma(-float(k), lo, fma(-float(k), hi, float(q)))
-        exact = Fraction(float(q)) - k * half_pi
-        worst = max(worst, abs(float(Fraction(r) - exact)))
-    assert worst < 1e-9
+        tm = fma(float(q), 0.63661977236758134308, magic)
+        kd = tm - magic
+        k = int(kd)
+        assert kd == k and abs(k - float(q) * 0.63661977236758134308) <= 0.5 + 1e-6
+        r = fma(-kd, hi, float(q))
+        worst = max(worst, abs(float(Fraction(r) - (Fraction(float(q)) - k * half_pi))))
+        worst_r = max(worst_r, abs(r))
+    assert worst < 2.7e-9 and worst_r < np.pi / 4 * (1 + 1e-7)
