@@ -114,7 +114,8 @@ __device__ __forceinline__ int sat_filter(const float A0, const float A1, const 
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     g = fmaxf(g, fabsf(pp[i]) - (fmaf(Qs[i], B2, fmaf(Qp[i].y, B1, Qp[i].x * B0)) + A[i]));
-  if (g > delta) return kSep;
+  // (no exit here: 5 % of the separated pairs would take it, and a warp waits for its slowest
+  // lane anyway)
   const float2 fudge = make_float2(1.0e-6f, 1.0e-6f);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -387,13 +388,13 @@ amb = false;
             // saved pose of the partner: 12 floats per lane as three 16-byte pieces (a lane
             // stride of 48 bytes is conflict free for 16-byte accesses)
             const float4* sv = reinterpret_cast<const float4*>(s_saved) + (sl * 32 + (int)lane) * 3;
-            const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];  // R0..R3 | R4..R7 | R8, c0, c1, c2
+            const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];  // R0 R3 R1 R4 | R2 R5 c0 c1 | R6 R7 R8 c2
             // partner's face axes against this box's bounding sphere, padded
-            const float d0 = cw[0] - s2.y, d1 = cw[1] - s2.z, d2 = cw[2] - s2.w;
+            const float d0 = cw[0] - s1.z, d1 = cw[1] - s1.w, d2 = cw[2] - s2.w;
             const float ra = bx.radius + delta;
-            const float y0 = fmaf(s1.z, d2, fmaf(s0.w, d1, s0.x * d0));
-            const float y1 = fmaf(s1.w, d2, fmaf(s1.x, d1, s0.y * d0));
-            const float y2 = fmaf(s2.x, d2, fmaf(s1.y, d1, s0.z * d0));
+            const float y0 = fmaf(s2.x, d2, fmaf(s0.y, d1, s0.x * d0));
+            const float y1 = fmaf(s2.y, d2, fmaf(s0.w, d1, s0.z * d0));
+            const float y2 = fmaf(s2.z, d2, fmaf(s1.y, d1, s1.x * d0));
             const bool sep = (fabsf(y0) > s_half[4 * sl + 0] + ra) |
                              (fabsf(y1) > s_half[4 * sl + 1] + ra) |
                              (fabsf(y2) > s_half[4 * sl + 2] + ra);
@@ -421,10 +422,9 @@ amb = false;
           const int sl = other - 64;
           const float4* sv = reinterpret_cast<const float4*>(s_saved) + (sl * 32 + owner) * 3;
           const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];
-          R2[0] = s0.x; R2[1] = s0.y; R2[2] = s0.z; R2[3] = s0.w;
-          R2[4] = s1.x; R2[5] = s1.y; R2[6] = s1.z; R2[7] = s1.w;
-          R2[8] = s2.x;
-          T2[0] = s2.y; T2[1] = s2.z; T2[2] = s2.w;
+          R2[0] = s0.x; R2[3] = s0.y; R2[1] = s0.z; R2[4] = s0.w;
+          R2[2] = s1.x; R2[5] = s1.y; T2[0] = s1.z; T2[1] = s1.w;
+          R2[6] = s2.x; R2[7] = s2.y; R2[8] = s2.z; T2[2] = s2.w;
           B0 = s_half[4 * sl]; B1 = s_half[4 * sl + 1]; B2 = s_half[4 * sl + 2];
           rB = s_half[4 * sl + 3];
         }
@@ -509,10 +509,15 @@ amb = false;
       }
 
       if (do_self && bx.save_slot >= 0) {
-        float4* sv = reinterpret_cast<float4*>(s_saved) + (bx.save_slot * 32 + (int)lane) * 3;
-        sv[0] = make_float4(Rw[0], Rw[1], Rw[2], Rw[3]);
-        sv[1] = make_float4(Rw[4], Rw[5], Rw[6], Rw[7]);
-        sv[2] = make_float4(Rw[8], cw[0], cw[1], cw[2]);
+        // order: (R0,R3) (R1,R4) (R2,R5) (c0,c1) (R6,R7) (R8,c2) - the register pairs the packed
+        // DH step and pose leave behind, stored as they are
+        float2* sv = reinterpret_cast<float2*>(s_saved) + (bx.save_slot * 32 + (int)lane) * 6;
+        sv[0] = make_float2(Rw[0], Rw[3]);
+        sv[1] = make_float2(Rw[1], Rw[4]);
+        sv[2] = make_float2(Rw[2], Rw[5]);
+        sv[3] = make_float2(cw[0], cw[1]);
+        sv[4] = make_float2(Rw[6], Rw[7]);
+        sv[5] = make_float2(Rw[8], cw[2]);
       }
     }
   }
