@@ -83,6 +83,7 @@ SIGNATURES = {
     "acro_fk_cc_f64_ws": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _D, _P, _I64, _P]),
     "acro_fk_cc_f32": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "acro_fk_cc_f64_host": (C.c_int, [_P, _P, _P, _I64, _P, _I64]),
+    "acro_fk_cc_f32_host": (C.c_int, [_P, _P, _P, _I64, _P, _I64]),
     "acro_jac_pos_f64": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "acro_jac_rpy_f64": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "acro_ik_kuka_f64": (C.c_int, [_P, _P, _I64, _P, _P, _P]),

@@ -831,14 +831,17 @@ struct HostPipe {
   int64_t chunk = 0;
   int ndof = 0;
   double* d_q[kSlots] = {};
+  float* d_q32[kSlots] = {};  // staging of FP32 joint rows (acro_fk_cc_f32_host), on first use
   uint32_t* d_mask[kSlots] = {};
   cudaStream_t st[kSlots] = {};
   void release() {
     for (int s = 0; s < kSlots; ++s) {
       if (d_q[s]) cudaFree(d_q[s]);
+      if (d_q32[s]) cudaFree(d_q32[s]);
       if (d_mask[s]) cudaFree(d_mask[s]);
       if (st[s]) cudaStreamDestroy(st[s]);
       d_q[s] = nullptr;
+      d_q32[s] = nullptr;
       d_mask[s] = nullptr;
       st[s] = nullptr;
     }
@@ -852,8 +855,10 @@ constexpr int kMaxPipeDevices = 64;
 HostPipe g_pipes[kMaxPipeDevices];
 }  // namespace
 
-int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
-                        int64_t n, uint32_t* mask_host, int64_t chunk) {
+// q_host: doubles (f32 == false) or floats (f32 == true; widened exactly on the device, so the
+// verdicts are those of the FP64 evaluation at the float-valued joint angles)
+static int host_pipeline(const AcroRobot* robot, const AcroScene* scene, const void* q_host,
+                         bool f32, int64_t n, uint32_t* mask_host, int64_t chunk, const char* what) {
   if (int rc = check_batch(robot, q_host, mask_host, n)) return rc;
   if (int rc = check_scene_device(scene)) return rc;
   if (n == 0) return 0;
@@ -877,20 +882,29 @@ int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const do
     if (e != cudaSuccess) {
       g_pipe.release();
       cudaGetLastError();
-      return cuda_fail(e, "acro_fk_cc_f64_host workspace");
+      return cuda_fail(e, "host pipeline workspace");
     }
     g_pipe.device = dev;
     g_pipe.chunk = chunk;
     g_pipe.ndof = ndof;
   }
+  for (int s = 0; s < kSlots && f32 && e == cudaSuccess; ++s)
+    if (!g_pipe.d_q32[s]) e = cudaMalloc(&g_pipe.d_q32[s], sizeof(float) * g_pipe.chunk * g_pipe.ndof);
+  if (e != cudaSuccess) return cuda_fail(e, "host pipeline workspace");
   int64_t done = 0;
   int slot = 0;
   while (done < n && e == cudaSuccess) {
     const int64_t m = (n - done) < chunk ? (n - done) : chunk;
     cudaStream_t st = g_pipe.st[slot];
     // work queued on a stream is ordered, so reusing the slot's buffers is safe
-    e = cudaMemcpyAsync(g_pipe.d_q[slot], q_host + done * ndof, sizeof(double) * m * ndof,
-                        cudaMemcpyHostToDevice, st);
+    if (f32) {
+      e = cudaMemcpyAsync(g_pipe.d_q32[slot], static_cast<const float*>(q_host) + done * ndof,
+                          sizeof(float) * m * ndof, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = launch_widen(g_pipe.d_q32[slot], g_pipe.d_q[slot], m * ndof, st);
+    } else {
+      e = cudaMemcpyAsync(g_pipe.d_q[slot], static_cast<const double*>(q_host) + done * ndof,
+                          sizeof(double) * m * ndof, cudaMemcpyHostToDevice, st);
+    }
     if (e == cudaSuccess)
       e = run_fk_cc_f64(robot, scene, g_pipe.d_q[slot], m, ACRO_Q_AOS, g_pipe.d_mask[slot], st);
     if (e == cudaSuccess)
@@ -903,7 +917,17 @@ int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const do
     cudaError_t e2 = cudaStreamSynchronize(g_pipe.st[s]);
     if (e == cudaSuccess) e = e2;
   }
-  return finish(e, "acro_fk_cc_f64_host");
+  return finish(e, what);
+}
+
+int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
+                        int64_t n, uint32_t* mask_host, int64_t chunk) {
+  return host_pipeline(robot, scene, q_host, false, n, mask_host, chunk, "acro_fk_cc_f64_host");
+}
+
+int acro_fk_cc_f32_host(const AcroRobot* robot, const AcroScene* scene, const float* q_host,
+                        int64_t n, uint32_t* mask_host, int64_t chunk) {
+  return host_pipeline(robot, scene, q_host, true, n, mask_host, chunk, "acro_fk_cc_f32_host");
 }
 
 int acro_jac_pos_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t q_layout,

@@ -177,6 +177,12 @@ int acro_fk_cc_f32(const AcroRobot* robot, const AcroScene* scene, const float* 
  * different host threads, calls on one device take turns.                       */
 int acro_fk_cc_f64_host(const AcroRobot* robot, const AcroScene* scene, const double* q_host,
                         int64_t n, uint32_t* mask_host, int64_t chunk);
+/* The same pipeline for FP32 joint values on the host (24 instead of 48 bytes per 6-dof
+ * configuration over PCIe - the link is what bounds the host path): the rows are widened
+ * exactly on the device, the verdicts are those of the FP64 evaluation at the float-valued
+ * joint angles.                                                                  */
+int acro_fk_cc_f32_host(const AcroRobot* robot, const AcroScene* scene, const float* q_host,
+                        int64_t n, uint32_t* mask_host, int64_t chunk);
 
 /* ---- K3/K4: Jacobians (robot.py:157-171; casadi AD in the reference) ----------
  * J_out (N,3,ndof) / (N,6,ndof) row-major.  The descriptor's base / tool tip are

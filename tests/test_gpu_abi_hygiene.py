@@ -137,3 +137,24 @@ def test_csr_rejects_misaligned_rows(gpu):
     _native.check(lib.acro_joint_solutions_csr_f64(k._handle(), scene.native_handle(), T.data_ptr(), 2, 32,
                                                    buf.data_ptr(), valid.data_ptr(), free.data_ptr(),
                                                    q_free.data_ptr(), 64 * 8, off.data_ptr(), st))
+
+
+def test_host_pipeline_with_fp32_rows(gpu):
+    """acro_fk_cc_f32_host: the FP32 rows are widened exactly, so the verdicts are those of the
+    FP64 path at the float-valued joint angles (ragged size, several chunks)."""
+    lib = _native.load()
+    k, scene = ab.Kuka(), scene16()
+    n = 777_777
+    q32 = random_configs(n, 6, seed=31).astype(np.float32)
+    qh = torch.from_numpy(q32).pin_memory()
+    mh = torch.zeros((n + 31) // 32, dtype=torch.int32).pin_memory()
+    _native.check(lib.acro_fk_cc_f32_host(k._handle(), scene.native_handle(), qh.data_ptr(), n,
+                                          mh.data_ptr(), 1 << 17))
+    want = k.is_in_collision_batch(q32.astype(np.float64), scene, packed=True)
+    assert np.array_equal(mh.numpy().view(np.uint32), want)
+    # and the FP64 host path on the same rows
+    qh64 = torch.from_numpy(q32.astype(np.float64)).pin_memory()
+    mh.zero_()
+    _native.check(lib.acro_fk_cc_f64_host(k._handle(), scene.native_handle(), qh64.data_ptr(), n,
+                                          mh.data_ptr(), 1 << 17))
+    assert np.array_equal(mh.numpy().view(np.uint32), want)
