@@ -18,7 +18,7 @@
 #define ACRO_JAC_POS_CTAS 5
 #endif
 #ifndef ACRO_IK_CTAS
-#define ACRO_IK_CTAS 4
+#define ACRO_IK_CTAS 6
 #endif
 #ifndef ACRO_JAC_RPY_CTAS
 #define ACRO_JAC_RPY_CTAS 4
@@ -250,15 +250,10 @@ __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, doub
   sol2[2] = atan2_reflected(sol1[2], sz);
 }
 
-// Kuka.ik for one pose (robot_examples.py:188-218).  T: 16 doubles row-major.
-// emit(k, pair) receives the two solutions of arm branch k (slots 2k and 2k+1, 12 doubles; NaN
-// when the branch does not exist) as soon as they are known - the caller parks them in shared
-// memory instead of keeping all 48 values in registers.  Returns the validity bit set
-// (slot = 2*arm + wrist).
-template <typename Emit>
-__device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const double* Tin,
-                                            Emit emit) {
-  Tf<double> Tw;
+// Pose in the arm's frame: Tw = tf_inverse(tf_base) @ T @ tf_inverse(tf_tool_tip)
+// (robot_examples.py:190-194, :14-23).  Tin: 16 doubles row-major.
+__device__ __forceinline__ void kuka_pose_in_arm_frame(const RobotDev<double>& rb, const double* Tin,
+                                                       Tf<double>& Tw) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     Tw.r[3 * r] = Tin[4 * r];
@@ -266,7 +261,7 @@ __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const do
     Tw.r[3 * r + 2] = Tin[4 * r + 2];
     Tw.p[r] = Tin[4 * r + 3];
   }
-  if (!rb.base_identity) {  // Tw = tf_inverse(tf_base) @ T   (:190-191, :14-23)
+  if (!rb.base_identity) {
     Tf<double> X;
     const double* b = rb.base;
     const double dx = Tw.p[0] - b[3], dy = Tw.p[1] - b[7], dz = Tw.p[2] - b[11];
@@ -279,7 +274,7 @@ __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const do
     }
     Tw = X;
   }
-  if (rb.has_tool_tip) {  // Tw = Tw @ tf_inverse(tf_tool_tip)   (:193-194)
+  if (rb.has_tool_tip) {
     Tf<double> X;
     const double* t = rb.tip;
 #pragma unroll
@@ -294,48 +289,86 @@ __device__ __forceinline__ unsigned kuka_ik(const RobotDev<double>& rb, const do
       X.p[i] = Tw.p[i] - (X.r[3 * i] * t[3] + X.r[3 * i + 1] * t[7] + X.r[3 * i + 2] * t[11]);
     Tw = X;
   }
-  const double a1 = rb.a[0], a2 = rb.a[1], d4 = rb.d[3], d6 = rb.d[5];
+}
+
+// One q1 branch of Kuka.ik (robot_examples.py:188-218 = arm_2.py:5-104 for the arm +
+// spherical_wrist.py:5-30 for the wrist): br = 0 is q1 = atan2(y, x), br = 1 the reflected
+// one.  The two elbow solutions of the branch (arm slots k = 2 br and 2 br + 1) with their two
+// wrist solutions each go to emit(kk, ...) (kk = 0, 1: 12 doubles, NaN when the branch is out
+// of reach); returns the 4 validity bits of the branch.  The arithmetic is that of the
+// whole-pose form, operation for operation (identities for the repeated transcendentals: see
+// arm2_ik / wrist_ik), so the two-threads-per-pose kernel returns the same bits.
+template <typename Emit>
+__device__ __forceinline__ unsigned kuka_ik_branch(const RobotDev<double>& rb, const Tf<double>& Tw,
+                                                   const int br, Emit emit) {
+  const double a1 = rb.a[0], a2 = rb.a[1], a3 = rb.d[3], d6 = rb.d[5];
   // wrist centre (:196-199)
-  const double px = Tw.p[0] - Tw.r[2] * d6;
-  const double py = Tw.p[1] - Tw.r[5] * d6;
-  const double pz = Tw.p[2] - Tw.r[8] * d6;
-  Arm2Sol S;
-  arm2_ik(px, py, pz, a1, a2, d4, S);
+  const double x = Tw.p[0] - Tw.r[2] * d6;
+  const double y = Tw.p[1] - Tw.r[5] * d6;
+  const double z = Tw.p[2] - Tw.r[8] * d6;
   const double nan = CUDART_NAN;
   const double half_pi_cos = 6.123233995736766e-17;  // np.cos(np.pi / 2)
-  unsigned valid = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool ok = (k < 2) ? S.pos : S.neg;
-    if (ok) {
-      const double q1 = S.q[k][0], q2 = S.q[k][1], q3 = S.q[k][2] + CUDART_PI / 2;  // :204
-      // orientation of Arm2(a1, a2, a3=d4).fk(q_arm)   (:207, robot_examples.py:114-131)
-      Tf<double> F;
-#pragma unroll
-      for (int e = 0; e < 9; ++e) F.r[e] = (e % 4 == 0) ? 1.0 : 0.0;
-      F.p[0] = F.p[1] = F.p[2] = 0.0;
-      // sines and cosines of the arm angles without evaluating them again: q1_neg is q1_pos
-      // plus half a turn; q2 = atan2(y2, x2); sin/cos(q3a + pi/2) = (c3, -s3) and
-      // sin/cos(-q3a + pi/2) = (c3, s3)
-      const int br = k >> 1;
-      const double sg = br ? -1.0 : 1.0;
-      tf_mul_dh<double>(F, sg * S.c1, sg * S.s1, half_pi_cos, 1.0, a1, 0.0);
-      const double h = sqrt(S.x2[k] * S.x2[k] + S.y2[k] * S.y2[k]);
-      const double inv = h > 0.0 ? 1.0 / h : 0.0;
-      tf_mul_dh<double>(F, h > 0.0 ? S.x2[k] * inv : 1.0, S.y2[k] * inv, 1.0, 0.0, a2, 0.0);
-      tf_mul_dh<double>(F, (k & 1) ? S.s3[br] : -S.s3[br], S.c3[br], half_pi_cos, 1.0, d4, 0.0);
-      double w1[3], w2[3];
-      wrist_ik(F.r, Tw.r, w1, w2);
-      emit(k, make_double2(q1, q2), make_double2(q3, w1[0]), make_double2(w1[1], w1[2]),
-           make_double2(q1, q2), make_double2(q3, w2[0]), make_double2(w2[1], w2[2]));
-      valid |= 3u << (2 * k);
-    } else {
-      const double2 nn = make_double2(nan, nan);
-      emit(k, nn, nn, nn, nn, nn, nn);
-    }
+  const double q1_pos = atan2(y, x);
+  const double q1 = br ? atan2_reflected(q1_pos, y) : q1_pos;
+  const double den = 2 * a2 * a3;
+  const double num = a1 * a1 - a2 * a2 - a3 * a3 + x * x + y * y + z * z;
+  const double L = sqrt(x * x + y * y);
+  double s1, c1;
+  sincos(q1_pos, &s1, &c1);
+  double c3 = br ? (num + 2 * a1 * s1 * y + 2 * a1 * x * c1) / den
+                 : (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
+  double s3 = 0;
+  if (!c3_branch(c3, s3)) {
+    const double2 nn = make_double2(nan, nan);
+    emit(0, nn, nn, nn, nn, nn, nn);
+    emit(1, nn, nn, nn, nn, nn, nn);
+    return 0u;
   }
-  return valid;
+  const double q3a = atan2(s3, c3);
+  const double e = a2 + a3 * c3;
+  // (y2, x2) of q2 = atan2(y2, x2) for the two elbow solutions (arm_2.py:47-104)
+  double y2[2], x2[2];
+  if (!br) {
+    y2[0] = -a3 * s3 * (L - a1) + z * e;
+    x2[0] = a3 * s3 * z + (L - a1) * e;
+    y2[1] = a3 * s3 * (L - a1) + z * e;
+    x2[1] = -a3 * s3 * z + (L - a1) * e;
+  } else {
+    y2[0] = a3 * s3 * (L + a1) + z * e;
+    x2[0] = a3 * s3 * z - (L + a1) * e;
+    y2[1] = -a3 * s3 * (L + a1) + z * e;
+    x2[1] = -a3 * s3 * z - (L + a1) * e;
+  }
+  const double sg = br ? -1.0 : 1.0;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    const double q2 = atan2(y2[kk], x2[kk]);
+    const double q3 = (kk ? -q3a : q3a) + CUDART_PI / 2;  // :204
+    // orientation of Arm2(a1, a2, a3=d4).fk(q_arm)   (:207, robot_examples.py:114-131), from
+    // the sines and cosines already at hand
+    Tf<double> F;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F.r[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    F.p[0] = F.p[1] = F.p[2] = 0.0;
+    tf_mul_dh<double>(F, sg * c1, sg * s1, half_pi_cos, 1.0, a1, 0.0);
+    const double h = sqrt(x2[kk] * x2[kk] + y2[kk] * y2[kk]);
+    const double inv = h > 0.0 ? 1.0 / h : 0.0;
+    tf_mul_dh<double>(F, h > 0.0 ? x2[kk] * inv : 1.0, y2[kk] * inv, 1.0, 0.0, a2, 0.0);
+    tf_mul_dh<double>(F, kk ? s3 : -s3, c3, half_pi_cos, 1.0, a3, 0.0);
+    double w1[3], w2[3];
+    wrist_ik(F.r, Tw.r, w1, w2);
+    emit(kk, make_double2(q1, q2), make_double2(q3, w1[0]), make_double2(w1[1], w1[2]),
+         make_double2(q1, q2), make_double2(q3, w2[0]), make_double2(w2[1], w2[2]));
+  }
+  return 0xFu;
 }
+
+// Two threads per pose (one per q1 branch): half the dependent FP64 chain and half the
+// registers per thread, 24 instead of 16 resident warps per SM - the kernel is bound by the
+// latency of its atan2 / sqrt chains, not by bandwidth or FP64 throughput.  Thread 2p + br
+// writes units [12 br, 12 br + 12) of row p of the staging tile (odd unit stride: conflict
+// free), the CTA then writes the tile as whole 128-byte lines.
+constexpr int kIkPoses = kTile / 2;  // poses per CTA
 
 template <bool WITH_CC>
 __global__ void __launch_bounds__(kTile, WITH_CC ? 1 : ACRO_IK_CTAS)
@@ -344,11 +377,15 @@ __global__ void __launch_bounds__(kTile, WITH_CC ? 1 : ACRO_IK_CTAS)
                    uint8_t* __restrict__ valid, uint8_t* __restrict__ free_mask, bool vec_in,
                    bool vec_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_scene = reinterpret_cast<double*>(smem_raw + row_stage_bytes<double, 48>());
-  const int64_t row0 = (int64_t)blockIdx.x * kTile;
-  const int64_t idx = row0 + threadIdx.x;
+  using RS = RowStage<double, 48>;
+  constexpr size_t kTileBytes = (size_t)kIkPoses * RS::STRIDE * 16;
+  double* s_scene = reinterpret_cast<double*>(smem_raw + kTileBytes);
+  const int64_t row0 = (int64_t)blockIdx.x * kIkPoses;
+  const int t = threadIdx.x;
+  const int pl = t >> 1, br = t & 1;  // local pose, q1 branch
+  const int64_t idx = row0 + pl;
   if (WITH_CC) {
-    for (int k = threadIdx.x; k < sc.n * kSceneStride; k += blockDim.x) s_scene[k] = sc.boxes[k];
+    for (int k = t; k < sc.n * kSceneStride; k += blockDim.x) s_scene[k] = sc.boxes[k];
     __syncthreads();
   }
   alignas(16) double Tin[16];
@@ -358,49 +395,52 @@ __global__ void __launch_bounds__(kTile, WITH_CC ? 1 : ACRO_IK_CTAS)
 #pragma unroll
     for (int k = 0; k < 16; ++k) Tin[k] = (k % 5 == 0) ? 1.0 : 0.0;
   }
-  // every arm branch's pair of solutions goes straight into this thread's row of the staging
-  // tile (row of 48 doubles = 24 16-byte units, odd unit stride: conflict free)
-  using RS = RowStage<double, 48>;
-  int4* s_tile = reinterpret_cast<int4*>(smem_raw);
+  Tf<double> Tw;
+  kuka_pose_in_arm_frame(rb, Tin, Tw);
   double2* s_tile2 = reinterpret_cast<double2*>(smem_raw);
   double* s_plain = reinterpret_cast<double*>(smem_raw);
-  const int t = threadIdx.x;
-  const unsigned vbits = kuka_ik(rb, Tin, [&](int k, double2 u0, double2 u1, double2 u2, double2 u3,
-                                              double2 u4, double2 u5) {
+  const unsigned bits4 = kuka_ik_branch(rb, Tw, br, [&](int kk, double2 u0, double2 u1, double2 u2,
+                                                        double2 u3, double2 u4, double2 u5) {
     const double2 u[6] = {u0, u1, u2, u3, u4, u5};
     if (vec_out) {
 #pragma unroll
-      for (int e = 0; e < 6; ++e) s_tile2[t * RS::STRIDE + 6 * k + e] = u[e];
+      for (int e = 0; e < 6; ++e) s_tile2[pl * RS::STRIDE + 12 * br + 6 * kk + e] = u[e];
     } else {
 #pragma unroll
       for (int e = 0; e < 6; ++e) {
-        s_plain[t * 49 + 12 * k + 2 * e] = u[e].x;
-        s_plain[t * 49 + 12 * k + 2 * e + 1] = u[e].y;
+        s_plain[pl * 49 + 24 * br + 12 * kk + 2 * e] = u[e].x;
+        s_plain[pl * 49 + 24 * br + 12 * kk + 2 * e + 1] = u[e].y;
       }
     }
   });
-  if (idx < n) valid[idx] = (uint8_t)vbits;
+  // the pose's 8 validity bits: branch 0 -> bits 0..3, branch 1 -> bits 4..7
+  const unsigned other = __shfl_xor_sync(0xffffffffu, bits4, 1);
+  const unsigned vbits = br ? (other | (bits4 << 4)) : (bits4 | (other << 4));
+  if (idx < n && br == 0) valid[idx] = (uint8_t)vbits;
   if (WITH_CC) {
     unsigned freebits = 0;
-    for (int sl = 0; sl < 8; ++sl) {  // path/path_pt_base.py:107-109
+    for (int k4 = 0; k4 < 4; ++k4) {  // this thread's four slots (path/path_pt_base.py:107-109)
+      const int sl = 4 * br + k4;
       const bool act = idx < n && ((vbits >> sl) & 1);
       double qv[6];
 #pragma unroll
       for (int e = 0; e < 6; ++e)
         qv[e] = !act ? 0.0
-                     : (vec_out ? reinterpret_cast<const double*>(s_tile + t * RS::STRIDE)[6 * sl + e]
-                                : s_plain[t * 49 + 6 * sl + e]);
+                     : (vec_out ? reinterpret_cast<const double*>(s_tile2 + pl * RS::STRIDE)[6 * sl + e]
+                                : s_plain[pl * 49 + 6 * sl + e]);
       Verdict<double, false> v;
       config_collision<double, 6, false>(rb, qv, s_scene, sc.n, 0.0, act, v);
       if (act && !v.hit) freebits |= 1u << sl;
     }
-    if (idx < n) free_mask[idx] = (uint8_t)freebits;
+    freebits |= __shfl_xor_sync(0xffffffffu, freebits, 1);
+    if (idx < n && br == 0) free_mask[idx] = (uint8_t)freebits;
   }
   // flat copy-out of the tile: whole 128-byte lines
   __syncthreads();
   const int64_t left = n - row0;
-  const int rows = left < kTile ? (int)left : kTile;
+  const int rows = left < kIkPoses ? (int)left : kIkPoses;
   if (vec_out) {
+    const int4* s_tile = reinterpret_cast<const int4*>(smem_raw);
     const int total = rows * RS::UNITS;
     for (int e = t; e < total; e += kTile) {
       const int r = e / RS::UNITS, c = e - r * RS::UNITS;
@@ -415,14 +455,17 @@ __global__ void __launch_bounds__(kTile, WITH_CC ? 1 : ACRO_IK_CTAS)
   }
 }
 
+constexpr size_t kIkTileBytes = (size_t)kIkPoses * (RowStage<double, 48>::STRIDE * 16 > 49 * 8
+                                                        ? RowStage<double, 48>::STRIDE * 16
+                                                        : 49 * 8);
+
 cudaError_t launch_ik_kuka(const RobotDev<double>& rb, const double* T, int64_t n, double* q_out,
                            uint8_t* valid, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const int64_t tiles = (n + kTile - 1) / kTile;
+  const int64_t tiles = (n + kIkPoses - 1) / kIkPoses;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const size_t smem = row_stage_bytes<double, 48>();
+  const size_t smem = kIkTileBytes;
   auto k = ik_kuka_kernel<false>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<(unsigned)tiles, kTile, smem, st>>>(rb, SceneView<double>{nullptr, 0}, T, n, q_out, valid,
                                           nullptr, aligned16(T), aligned16(q_out));
   count_launch();
@@ -433,9 +476,9 @@ cudaError_t launch_ik_kuka_cc(const RobotDev<double>& rb, SceneView<double> sc, 
                               int64_t n, double* q_out, uint8_t* valid, uint8_t* free_mask,
                               cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const int64_t tiles = (n + kTile - 1) / kTile;
+  const int64_t tiles = (n + kIkPoses - 1) / kIkPoses;
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const size_t smem = row_stage_bytes<double, 48>() + sizeof(double) * (sc.n * kSceneStride);
+  const size_t smem = kIkTileBytes + sizeof(double) * (sc.n * kSceneStride);
   auto k = ik_kuka_kernel<true>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<(unsigned)tiles, kTile, smem, st>>>(rb, sc, T, n, q_out, valid, free_mask, aligned16(T),
