@@ -342,14 +342,16 @@ def path_grid_arrays(path):
     return out
 
 
-def joint_solutions_csr(robot, T, scene, return_all=False):
+def joint_solutions_csr(robot, T, scene, return_all=False, trim=True):
     """Planner inner loop for a whole path.
 
     ``T``: (P, S, 4, 4) sampled poses (P path points, S samples each; numpy or CUDA tensor).
     Returns ``(q_free, offsets)``: ``q_free[offsets[p]:offsets[p+1]]`` are the collision-free
     IK solutions of path point ``p`` in the reference's order.  numpy in -> numpy out, CUDA
     tensor in -> CUDA tensors out.  ``return_all`` also returns (q_all (P,S,8,6), valid (P,S),
-    free (P,S)) branch bit masks."""
+    free (P,S)) branch bit masks.  ``trim=False`` (CUDA input only) skips the host
+    synchronisation that reads the row count: ``q_free`` then has the full capacity of ``8 P S``
+    rows, of which the first ``offsets[-1]`` are defined - the call stays asynchronous."""
     host = not isinstance(T, torch.Tensor) or not T.is_cuda
     device.require_cuda()
     Td = torch.as_tensor(np.asarray(T) if not isinstance(T, torch.Tensor) else T,
@@ -372,8 +374,9 @@ def joint_solutions_csr(robot, T, scene, return_all=False):
         ) if S > 0 else 0,
         "acro_joint_solutions_csr_f64",
     )
-    total = int(offsets[-1].item())
-    q_free = q_free[:total]
+    if trim or host:
+        total = int(offsets[-1].item())
+        q_free = q_free[:total]
     out = (device.to_host(q_free, host), device.to_host(offsets, host))
     if return_all:
         out += (device.to_host(q_all[:n].reshape(P, S, 8, 6), host),

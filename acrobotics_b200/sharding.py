@@ -219,7 +219,7 @@ def is_path_in_collision_discrete_sharded(robot, q_start, q_goal, scene, max_q_s
 
 
 def joint_solutions_csr_sharded(robot, T, scene, group=None, gather_solutions: bool = False,
-                                solve_local: Callable = None):
+                                solve_local: Callable = None, trim: bool = True):
     """Planner sweep (``path_to_joint_solutions``, reference planning/sampling_based.py:94-106)
     over the ranks: ``T`` (P, S, 4, 4) is held by every rank, rank ``r`` evaluates the path
     points ``split_range(P, r, world)`` (IK -> collision filter -> CSR compaction on its GPU)
@@ -228,7 +228,9 @@ def joint_solutions_csr_sharded(robot, T, scene, group=None, gather_solutions: b
     Returns a dict: ``counts`` (P,) int64 and ``free`` (P, S) uint8 on every rank;
     ``q_local`` / ``offsets_local`` / ``points`` = this rank's CSR block and its point range;
     with ``gather_solutions`` also ``q_free`` / ``offsets`` = the whole CSR on every rank
-    (padded all-gather of the rows, then one compaction)."""
+    (padded all-gather of the rows, then one compaction).  ``trim=False``: ``q_local`` keeps its
+    full capacity (rows beyond ``offsets_local[-1]`` undefined) and nothing is read back to the
+    host, so the call is asynchronous."""
     from .path.path_pt import joint_solutions_csr
 
     rank, world = _rank_world(group)
@@ -236,7 +238,8 @@ def joint_solutions_csr_sharded(robot, T, scene, group=None, gather_solutions: b
     lo, hi = split_range(P, rank, world)
     per = -(-P // world) if world > 1 else P
     dev = T.device if isinstance(T, torch.Tensor) else "cpu"
-    solve = solve_local or (lambda Tl: joint_solutions_csr(robot, Tl, scene, return_all=True))
+    solve = solve_local or (lambda Tl: joint_solutions_csr(robot, Tl, scene, return_all=True,
+                                                           trim=trim or gather_solutions))
     if hi > lo:
         q_local, off_local, _, _, free_local = solve(T[lo:hi])
     else:

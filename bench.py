@@ -406,7 +406,8 @@ def run_ours(args):
         res = {}
 
         def c5_step():
-            res["r"] = sharding.joint_solutions_csr_sharded(robot, T, scene)
+            # trim=False: the row count stays on the device, the call is asynchronous
+            res["r"] = sharding.joint_solutions_csr_sharded(robot, T, scene, trim=False)
 
         cms = _time_steps(torch, dist, world, c5_step, max(2, args.steps // 2), 2)
         free_total = int(res["r"]["counts"].sum().item())
