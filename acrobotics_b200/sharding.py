@@ -13,6 +13,10 @@ the contiguous rows ``[r * N / G, (r + 1) * N / G)`` of SURVEY §8e.  With ``pie
 kernel of piece ``k + 1`` runs while piece ``k`` is all-gathered (the blocks of one piece are
 adjacent in the global mask, so every gather is one in-place ``all_gather_into_tensor``: the
 kernel writes its words straight into its block of the gather buffer and nothing is repacked).
+Measured on eight B200s: the fused kernel is persistent and fills every SM, so
+the NCCL kernel of piece ``k`` waits for the compute kernel of piece ``k + 1`` instead of
+overlapping it - ``pieces = 2`` is 4 % slower than ``pieces = 1``, which is therefore the
+default; the pieces layout stays for callers whose local kernel leaves SMs free.
 
 Nothing here computes collisions: the callers pass the callable that runs the fused
 FK -> collision kernel on the local rows.
