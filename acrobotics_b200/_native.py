@@ -97,6 +97,7 @@ SIGNATURES = {
     "acro_filter_tolerance": (C.c_int, [_P, _P, C.POINTER(_D)]),
     "acro_measure_filter_error": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "acro_measure_fma_peak": (C.c_int, [_I32, _I32, C.POINTER(_D), C.POINTER(_D)]),
+    "acro_math_probe_f64": (C.c_int, [_I32, _P, _P, _P, _P, _I64, _P]),
 }
 
 _lib = None

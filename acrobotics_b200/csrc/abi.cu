@@ -1126,6 +1126,15 @@ int acro_measure_filter_error(const AcroRobot* robot, const AcroScene* scene, co
                 "acro_measure_filter_error");
 }
 
+int acro_math_probe_f64(int32_t fn, const double* a, const double* b, double* out0, double* out1,
+                        int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!a || !out0))) return fail(ACRO_E_INVALID, "bad arguments");
+  if (fn < 0 || fn > 4) return fail(ACRO_E_INVALID, "fn must be 0..4");
+  if (n > 0 && ((fn == 0 && !out1) || ((fn == 1 || fn == 3) && !b)))
+    return fail(ACRO_E_INVALID, "missing operand / output array");
+  return finish(launch_math_probe(fn, a, b, out0, out1, n, as_stream(stream)), "acro_math_probe_f64");
+}
+
 int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms) {
   if (!tflops || !ms || iters <= 0) return fail(ACRO_E_INVALID, "bad arguments");
   return finish(measure_fma_peak(fp64 != 0, iters, tflops, ms), "acro_measure_fma_peak");
@@ -1137,6 +1146,37 @@ int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* m
 // FMA-chain micro-benchmark (compute-roofline denominator)
 // ---------------------------------------------------------------------------
 namespace acro {
+
+// element-wise evaluation of the lean FP64 functions of acro_math.cuh (test hook)
+__global__ void __launch_bounds__(256)
+    math_probe_kernel(int fn, const double* __restrict__ a, const double* __restrict__ b,
+                      double* __restrict__ out0, double* __restrict__ out1, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i];
+  if (fn == 0) {
+    double s, c;
+    sincos_lean(x, &s, &c);
+    out0[i] = s;
+    out1[i] = c;
+  } else if (fn == 1) {
+    out0[i] = atan2_lean(x, b[i]);
+  } else if (fn == 2) {
+    out0[i] = sqrt_lean(x);
+  } else if (fn == 3) {
+    out0[i] = div_lean(x, b[i]);
+  } else {
+    out0[i] = rcp_lean(x);
+  }
+}
+
+cudaError_t launch_math_probe(int fn, const double* a, const double* b, double* out0, double* out1,
+                              int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fn, a, b, out0, out1, n);
+  count_launch();
+  return cudaGetLastError();
+}
 
 template <typename real>
 __global__ void __launch_bounds__(256) fma_chain_kernel(real* out, int iters, real a, real b) {

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/acro_b200.h"
+#include "acro_math.cuh"
 
 namespace acro {
 
@@ -106,7 +107,7 @@ template <typename real>
 __device__ __forceinline__ void sincos_t(real x, real* s, real* c);
 template <>
 __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) {
-  sincos(x, s, c);
+  sincos_f64(x, s, c);  // acro_math.cuh
 }
 // FP32 chain (poses good to 1e-5): Cody-Waite reduction by pi/2 in three exact steps and the
 // Cephes minimax polynomials on [-pi/4, pi/4] (abs error ~1.5e-7) for |x| <= 1024; the library

@@ -95,6 +95,8 @@ cudaError_t launch_shortest_path(const double* q, int ndof, const int64_t* offse
                                  cudaStream_t st);
 
 cudaError_t measure_fma_peak(bool fp64, int iters, double* tflops, double* ms);
+cudaError_t launch_math_probe(int fn, const double* a, const double* b, double* out0, double* out1,
+                              int64_t n, cudaStream_t st);
 
 #define ACRO_DISPATCH_NDOF(ndof, ...)            \
   switch (ndof) {                                \

@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(kTile)
     T = E;
   }
   // robot.py:73-77 (r_z uses T[0,1] and T[2,2]: the reference's own formula)
-  const double s = sqrt(T.r[0] * T.r[0] + T.r[1] * T.r[1]);
+  const double s = sqrt_f64(T.r[0] * T.r[0] + T.r[1] * T.r[1]);
   alignas(16) double row[6];
   row[0] = T.p[0];
   row[1] = T.p[1];
   row[2] = T.p[2];
-  row[3] = atan2(-T.r[5], T.r[8]);
-  row[4] = atan2(T.r[2], s);
-  row[5] = atan2(-T.r[1], T.r[8]);
+  row[3] = atan2_f64(-T.r[5], T.r[8]);
+  row[4] = atan2_f64(T.r[2], s);
+  row[5] = atan2_f64(-T.r[1], T.r[8]);
   stage_store_rows<double, 6>(smem_raw, row, out, row0, n, 6, 0, vec_out);
 }
 

@@ -84,10 +84,10 @@ __global__ void __launch_bounds__(kTile, RPY ? ACRO_JAC_RPY_CTAS : ACRO_JAC_POS_
   alignas(16) double row[W + (W & 1)];
   // angle terms of robot.py:138-144, differentiated by the chain rule
   const double T00 = T.r[0], T01 = T.r[1], T02 = T.r[2], T12 = T.r[5], T22 = T.r[8];
-  const double s = sqrt(T00 * T00 + T01 * T01);
-  const double inv_x = 1.0 / (T22 * T22 + T12 * T12);  // r_x = atan2(-T12, T22)
-  const double inv_y = 1.0 / (s * s + T02 * T02);      // r_y = atan2( T02, s)
-  const double inv_z = 1.0 / (T22 * T22 + T01 * T01);  // r_z = atan2(-T01, T22)
+  const double s = sqrt_f64(T00 * T00 + T01 * T01);
+  const double inv_x = 1.0 / (T22 * T22 + T12 * T12);  // r_x = atan2_f64(-T12, T22)
+  const double inv_y = 1.0 / (s * s + T02 * T02);      // r_y = atan2_f64( T02, s)
+  const double inv_z = 1.0 / (T22 * T22 + T01 * T01);  // r_z = atan2_f64(-T01, T22)
 #pragma unroll
   for (int i = 0; i < NDOF; ++i) {
     const bool prismatic = (rb.prismatic_mask >> i) & 1;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTile, RPY ? ACRO_JAC_RPY_CTAS : ACRO_JAC_POS_
         const double d12 = z2 * T.r[2] - z0 * T.r[8];
         const double d22 = z0 * T.r[5] - z1 * T.r[2];
         const double ds = (T00 * d00 + T01 * d01) / s;
-        // d atan2(y, x) = (x dy - y dx) / (x^2 + y^2)
+        // d atan2_f64(y, x) = (x dy - y dx) / (x^2 + y^2)
         row[3 * NDOF + i] = (T22 * (-d12) - (-T12) * d22) * inv_x;
         row[4 * NDOF + i] = (s * d02 - T02 * ds) * inv_y;
         row[5 * NDOF + i] = (T22 * (-d01) - (-T01) * d22) * inv_z;
@@ -153,7 +153,7 @@ struct Arm2Sol {
   double q[4][3];  // [pos_a, pos_b, neg_a, neg_b] x (q1, q2, q3)
   bool pos, neg;
   // by-products reused by kuka_ik: sin/cos(q1_pos), cos/sin(q3) per q1 branch, and the
-  // (y, x) arguments of the q2 = atan2(y, x) of every solution
+  // (y, x) arguments of the q2 = atan2_f64(y, x) of every solution
   double s1, c1, c3[2], s3[2], y2[4], x2[4];
 };
 
@@ -162,7 +162,7 @@ __device__ __forceinline__ bool c3_branch(double& c3, double& s3) {
   const double tol = 1e-6;
   if (c3 > (1 + tol) || c3 < -(1 + tol)) return false;
   if (c3 > (1 - tol) || c3 < -(1 - tol)) c3 = c3 > 0 ? 1.0 : -1.0;  // np.sign
-  s3 = sqrt(1 - c3 * c3);
+  s3 = sqrt_f64(1 - c3 * c3);
   return true;
 }
 
@@ -176,20 +176,20 @@ __device__ __forceinline__ double atan2_reflected(double r, double y) {
 
 // inverse_kinematics/arm_2.py:5-104.  Transcendentals are evaluated once and reused through
 // exact identities (the reference recomputes them): sin/cos(q1_neg) = -sin/cos(q1_pos),
-// atan2(-s3, c3) = -atan2(s3, c3), cos(q3b) = c3 and sin(q3a) = s3 (arm_2.py:65, :76-77).
+// atan2_f64(-s3, c3) = -atan2_f64(s3, c3), cos(q3b) = c3 and sin(q3a) = s3 (arm_2.py:65, :76-77).
 __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1, double a2,
                                         double a3, Arm2Sol& S) {
   const double nan = CUDART_NAN;
-  const double q1_pos = atan2(y, x);
+  const double q1_pos = atan2_f64(y, x);
   const double q1_neg = atan2_reflected(q1_pos, y);
   const double den = 2 * a2 * a3;
   const double num = a1 * a1 - a2 * a2 - a3 * a3 + x * x + y * y + z * z;
-  const double L = sqrt(x * x + y * y);
+  const double L = sqrt_f64(x * x + y * y);
 #pragma unroll
   for (int k = 0; k < 4; ++k) S.q[k][0] = S.q[k][1] = S.q[k][2] = nan;
 
   double s1, c1, c3, s3 = 0;
-  sincos(q1_pos, &s1, &c1);
+  sincos_f64(q1_pos, &s1, &c1);
   S.s1 = s1;
   S.c1 = c1;
   c3 = (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1,
   S.c3[0] = c3;
   S.s3[0] = s3;
   if (S.pos) {
-    const double q3a = atan2(s3, c3);
+    const double q3a = atan2_f64(s3, c3);
     const double cc = c3, ss = s3;
     S.q[0][0] = q1_pos;
     S.y2[0] = -a3 * ss * (L - a1) + z * (a2 + a3 * cc);
@@ -207,15 +207,15 @@ __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1,
     S.y2[1] = a3 * ss * (L - a1) + z * (a2 + a3 * cc);
     S.x2[1] = -a3 * ss * z + (L - a1) * (a2 + a3 * cc);
     S.q[1][2] = -q3a;
-    S.q[0][1] = atan2(S.y2[0], S.x2[0]);
-    S.q[1][1] = atan2(S.y2[1], S.x2[1]);
+    S.q[0][1] = atan2_f64(S.y2[0], S.x2[0]);
+    S.q[1][1] = atan2_f64(S.y2[1], S.x2[1]);
   }
   c3 = (num + 2 * a1 * s1 * y + 2 * a1 * x * c1) / den;
   S.neg = c3_branch(c3, s3);
   S.c3[1] = c3;
   S.s3[1] = s3;
   if (S.neg) {
-    const double q3a = atan2(s3, c3);
+    const double q3a = atan2_f64(s3, c3);
     const double ss = s3, cc = c3;
     S.q[2][0] = q1_neg;
     S.y2[2] = a3 * ss * (L + a1) + z * (a2 + a3 * cc);
@@ -225,14 +225,14 @@ __device__ __forceinline__ void arm2_ik(double x, double y, double z, double a1,
     S.y2[3] = -a3 * ss * (L + a1) + z * (a2 + a3 * cc);
     S.x2[3] = -a3 * ss * z - (L + a1) * (a2 + a3 * cc);
     S.q[3][2] = -q3a;
-    S.q[2][1] = atan2(S.y2[2], S.x2[2]);
-    S.q[3][1] = atan2(S.y2[3], S.x2[3]);
+    S.q[2][1] = atan2_f64(S.y2[2], S.x2[2]);
+    S.q[3][1] = atan2_f64(S.y2[3], S.x2[3]);
   }
 }
 
 // inverse_kinematics/spherical_wrist.py:5-30; Rb, R row-major 3x3.  The mirrored solution
-// follows from the first one: atan2(-a1, -a0) and atan2(-sz, nz) are reflections,
-// atan2(-A, a2) = -atan2(A, a2).
+// follows from the first one: atan2_f64(-a1, -a0) and atan2_f64(-sz, nz) are reflections,
+// atan2_f64(-A, a2) = -atan2_f64(A, a2).
 __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, double* sol1,
                                          double* sol2) {
   // Rrel = Rb^T R ; a = Rrel[:,2], s_z = Rrel[2,1], n_z = Rrel[2,0]
@@ -241,10 +241,10 @@ __device__ __forceinline__ void wrist_ik(const double* Rb, const double* R, doub
   const double a2 = Rb[2] * R[2] + Rb[5] * R[5] + Rb[8] * R[8];
   const double sz = Rb[2] * R[1] + Rb[5] * R[4] + Rb[8] * R[7];
   const double nz = Rb[2] * R[0] + Rb[5] * R[3] + Rb[8] * R[6];
-  const double A = sqrt(a0 * a0 + a1 * a1);
-  sol1[0] = atan2(a1, a0);
-  sol1[1] = atan2(A, a2);
-  sol1[2] = atan2(sz, -nz);
+  const double A = sqrt_f64(a0 * a0 + a1 * a1);
+  sol1[0] = atan2_f64(a1, a0);
+  sol1[1] = atan2_f64(A, a2);
+  sol1[2] = atan2_f64(sz, -nz);
   sol2[0] = atan2_reflected(sol1[0], a1);
   sol2[1] = -sol1[1];
   sol2[2] = atan2_reflected(sol1[2], sz);
@@ -292,7 +292,7 @@ __device__ __forceinline__ void kuka_pose_in_arm_frame(const RobotDev<double>& r
 }
 
 // One q1 branch of Kuka.ik (robot_examples.py:188-218 = arm_2.py:5-104 for the arm +
-// spherical_wrist.py:5-30 for the wrist): br = 0 is q1 = atan2(y, x), br = 1 the reflected
+// spherical_wrist.py:5-30 for the wrist): br = 0 is q1 = atan2_f64(y, x), br = 1 the reflected
 // one.  The two elbow solutions of the branch (arm slots k = 2 br and 2 br + 1) with their two
 // wrist solutions each go to emit(kk, ...) (kk = 0, 1: 12 doubles, NaN when the branch is out
 // of reach); returns the 4 validity bits of the branch.  The arithmetic is that of the
@@ -308,13 +308,13 @@ __device__ __forceinline__ unsigned kuka_ik_branch(const RobotDev<double>& rb, c
   const double z = Tw.p[2] - Tw.r[8] * d6;
   const double nan = CUDART_NAN;
   const double half_pi_cos = 6.123233995736766e-17;  // np.cos(np.pi / 2)
-  const double q1_pos = atan2(y, x);
+  const double q1_pos = atan2_f64(y, x);
   const double q1 = br ? atan2_reflected(q1_pos, y) : q1_pos;
   const double den = 2 * a2 * a3;
   const double num = a1 * a1 - a2 * a2 - a3 * a3 + x * x + y * y + z * z;
-  const double L = sqrt(x * x + y * y);
+  const double L = sqrt_f64(x * x + y * y);
   double s1, c1;
-  sincos(q1_pos, &s1, &c1);
+  sincos_f64(q1_pos, &s1, &c1);
   double c3 = br ? (num + 2 * a1 * s1 * y + 2 * a1 * x * c1) / den
                  : (num - 2 * a1 * s1 * y - 2 * a1 * x * c1) / den;
   double s3 = 0;
@@ -324,9 +324,9 @@ __device__ __forceinline__ unsigned kuka_ik_branch(const RobotDev<double>& rb, c
     emit(1, nn, nn, nn, nn, nn, nn);
     return 0u;
   }
-  const double q3a = atan2(s3, c3);
+  const double q3a = atan2_f64(s3, c3);
   const double e = a2 + a3 * c3;
-  // (y2, x2) of q2 = atan2(y2, x2) for the two elbow solutions (arm_2.py:47-104)
+  // (y2, x2) of q2 = atan2_f64(y2, x2) for the two elbow solutions (arm_2.py:47-104)
   double y2[2], x2[2];
   if (!br) {
     y2[0] = -a3 * s3 * (L - a1) + z * e;
@@ -342,7 +342,7 @@ __device__ __forceinline__ unsigned kuka_ik_branch(const RobotDev<double>& rb, c
   const double sg = br ? -1.0 : 1.0;
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk) {
-    const double q2 = atan2(y2[kk], x2[kk]);
+    const double q2 = atan2_f64(y2[kk], x2[kk]);
     const double q3 = (kk ? -q3a : q3a) + CUDART_PI / 2;  // :204
     // orientation of Arm2(a1, a2, a3=d4).fk(q_arm)   (:207, robot_examples.py:114-131), from
     // the sines and cosines already at hand
@@ -351,7 +351,7 @@ __device__ __forceinline__ unsigned kuka_ik_branch(const RobotDev<double>& rb, c
     for (int i = 0; i < 9; ++i) F.r[i] = (i % 4 == 0) ? 1.0 : 0.0;
     F.p[0] = F.p[1] = F.p[2] = 0.0;
     tf_mul_dh<double>(F, sg * c1, sg * s1, half_pi_cos, 1.0, a1, 0.0);
-    const double h = sqrt(x2[kk] * x2[kk] + y2[kk] * y2[kk]);
+    const double h = sqrt_f64(x2[kk] * x2[kk] + y2[kk] * y2[kk]);
     const double inv = h > 0.0 ? 1.0 / h : 0.0;
     tf_mul_dh<double>(F, h > 0.0 ? x2[kk] * inv : 1.0, y2[kk] * inv, 1.0, 0.0, a2, 0.0);
     tf_mul_dh<double>(F, kk ? s3 : -s3, c3, half_pi_cos, 1.0, a3, 0.0);
@@ -548,14 +548,14 @@ __global__ void __launch_bounds__(kTile)
   double c3 = (Lps - l2 * l2 - l3 * l3) / (2 * l2 * l3), s3 = 0;
   const bool ok = c3_branch(c3, s3);
   if (ok) {
-    const double t3_1 = atan2(s3, c3), t3_2 = atan2(-s3, c3);
-    const double Lxy = sqrt(px * px + py * py);
+    const double t3_1 = atan2_f64(s3, c3), t3_2 = atan2_f64(-s3, c3);
+    const double Lxy = sqrt_f64(px * px + py * py);
     const double A = l2 + l3 * c3, B = l3 * s3;
-    const double t2_1 = atan2(pz * A - Lxy * B, Lxy * A + pz * B);
-    const double t2_2 = atan2(pz * A + Lxy * B, -Lxy * A + pz * B);
-    const double t2_3 = atan2(pz * A + Lxy * B, Lxy * A - pz * B);
-    const double t2_4 = atan2(pz * A - Lxy * B, -Lxy * A - pz * B);
-    const double t1_1 = atan2(py, px), t1_2 = atan2(-py, -px);
+    const double t2_1 = atan2_f64(pz * A - Lxy * B, Lxy * A + pz * B);
+    const double t2_2 = atan2_f64(pz * A + Lxy * B, -Lxy * A + pz * B);
+    const double t2_3 = atan2_f64(pz * A + Lxy * B, Lxy * A - pz * B);
+    const double t2_4 = atan2_f64(pz * A - Lxy * B, -Lxy * A - pz * B);
+    const double t1_1 = atan2_f64(py, px), t1_2 = atan2_f64(-py, -px);
     sol[0][0] = t1_1; sol[0][1] = t2_1; sol[0][2] = t3_1;
     sol[1][0] = t1_1; sol[1][1] = t2_3; sol[1][2] = t3_2;
     sol[2][0] = t1_2; sol[2][1] = t2_2; sol[2][2] = t3_1;

@@ -179,7 +179,8 @@ class ClockSampler:
 # GPU arm
 # ----------------------------------------------------------------------------
 K2_SOURCES = ["acrobotics_b200/csrc/fk_cc_filt.cu", "acrobotics_b200/csrc/acro_filter.cuh",
-              "acrobotics_b200/csrc/acro_device.cuh", "acrobotics_b200/csrc/acro_collide.cuh"]
+              "acrobotics_b200/csrc/acro_device.cuh", "acrobotics_b200/csrc/acro_collide.cuh",
+              "acrobotics_b200/csrc/acro_math.cuh"]
 
 
 def k2_source_hash():

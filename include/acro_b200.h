@@ -255,6 +255,11 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
  * DFMA / FFMA chain micro-benchmark: the compute-roofline denominator.  Returns
  * achieved TFLOP/s (FMA = 2 flop) in *tflops; runs on the current device.        */
 int acro_measure_fma_peak(int32_t fp64, int32_t iters, double* tflops, double* ms);
+/* Test hook for the FP64 elementary functions the kernels use in place of the CUDA library's
+ * (csrc/acro_math.cuh): element-wise over device arrays.  fn = 0 sincos(a) -> out0 = sin,
+ * out1 = cos; 1 atan2(a, b); 2 sqrt(a); 3 a / b; 4 1 / a (3, 4: normal b / a only).          */
+int acro_math_probe_f64(int32_t fn, const double* a, const double* b, double* out0, double* out1,
+                        int64_t n, void* stream);
 /* The filtered K2 kernel decides in FP32 with a tolerance delta.  These two
  * calls expose the evidence: the tolerance used for a (robot, scene) pair, and the measured
  * distance between the FP32 and FP64 decision quantities over a batch of configurations

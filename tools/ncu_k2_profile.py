@@ -83,7 +83,8 @@ def source_hash():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     h = hashlib.sha256()
     for rel in ["acrobotics_b200/csrc/fk_cc_filt.cu", "acrobotics_b200/csrc/acro_filter.cuh",
-                "acrobotics_b200/csrc/acro_device.cuh", "acrobotics_b200/csrc/acro_collide.cuh"]:
+                "acrobotics_b200/csrc/acro_device.cuh", "acrobotics_b200/csrc/acro_collide.cuh",
+                "acrobotics_b200/csrc/acro_math.cuh"]:
         with open(os.path.join(root, rel), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
