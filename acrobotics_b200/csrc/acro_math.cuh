@@ -108,18 +108,22 @@ __device__ __forceinline__ double rcp_lean(double d) {
   return fma(r, e, r);
 }
 
-// n / d, correctly rounded up to an ulp, same preconditions on d
+// n / d, correctly rounded up to an ulp, same preconditions on d.  The quotient estimate is
+// refined alongside the reciprocal (five dependent operations behind the hardware estimate).
 __device__ __forceinline__ double div_lean(double n, double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   double e = fma(-d, r, 1.0);
+  const double q0 = n * r;
   e = fma(e, e, e);
+  const double q = fma(q0, e, q0);
   r = fma(r, e, r);
-  const double q = n * r;
   const double rem = fma(-d, q, n);
   return fma(rem, r, q);
 }
 
+// atan2 without data-dependent branches on the common path: the octant is folded into one
+// division and one affine map of the reduced angle, selections act on 0 / 1 / 2 factors.
 __device__ __forceinline__ double atan2_lean(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool steep = ay > ax;  // false when either is NaN: a NaN |x| then stays in mx
@@ -129,27 +133,36 @@ __device__ __forceinline__ double atan2_lean(double y, double x) {
   // mn propagates through the arithmetic below
   const unsigned eh = (unsigned)__double2hiint(mx);
   if (eh - 0x20b00000u >= 0x3e800000u) return atan2(y, x);
-  // one division: t = mn / mx, or with the quarter turn folded in, (mn - mx) / (mn + mx)
+  // one division: t = mn / mx, or with the eighth turn folded in, (mn - mx) / (mn + mx)
   const bool fold = mn > 0.41421356237309503 * mx;
-  const double num = fold ? mn - mx : mn;
-  const double den = fold ? mn + mx : mx;
+  const double f = __hiloint2double(fold ? 0x3ff00000 : 0, 0);  // 1.0 or 0.0
+  const double num = fma(-f, mx, mn);
+  const double den = fma(f, mn, mx);
   const double t = div_lean(num, den);
   const double z = t * t;
-  double p = fma(z, kLeanAtan[11], kLeanAtan[10]);
-  p = fma(z, p, kLeanAtan[9]);
-  p = fma(z, p, kLeanAtan[8]);
-  p = fma(z, p, kLeanAtan[7]);
-  p = fma(z, p, kLeanAtan[6]);
-  p = fma(z, p, kLeanAtan[5]);
-  p = fma(z, p, kLeanAtan[4]);
-  p = fma(z, p, kLeanAtan[3]);
-  p = fma(z, p, kLeanAtan[2]);
-  p = fma(z, p, kLeanAtan[1]);
-  p = fma(z, p, kLeanAtan[0]);
-  double a = fma(t * z, p, t);  // atan(t), |t| <= 0.4143
-  if (fold) a = kLeanAtan[12] + (a + kLeanAtan[13]);
-  if (steep) a = kLeanAtan[14] - (a - kLeanAtan[15]);
-  if (__double2hiint(x) < 0) a = kLeanAtan[16] - (a - kLeanAtan[17]);
+  // atan(t) = t + t z p(z), |t| <= 0.4143; p split into its even and odd halves in w = z^2
+  // (two chains of five instead of one of eleven)
+  const double w = z * z;
+  double pe = fma(w, kLeanAtan[10], kLeanAtan[8]);
+  double po = fma(w, kLeanAtan[11], kLeanAtan[9]);
+  pe = fma(w, pe, kLeanAtan[6]);
+  po = fma(w, po, kLeanAtan[7]);
+  pe = fma(w, pe, kLeanAtan[4]);
+  po = fma(w, po, kLeanAtan[5]);
+  pe = fma(w, pe, kLeanAtan[2]);
+  po = fma(w, po, kLeanAtan[3]);
+  pe = fma(w, pe, kLeanAtan[0]);
+  po = fma(w, po, kLeanAtan[1]);
+  const double p = fma(z, po, pe);
+  double a = fma(t * z, p, t);
+  a = fma(f, kLeanAtan[12], fma(f, kLeanAtan[13], a));  // + pi/4 when folded: a in [0, pi/4]
+  // octant: result = m pi/2 + s a with (m, s) = (0, +) | (1, -) steep | (2, -) x < 0 |
+  // (1, +) both
+  const bool negx = __double2hiint(x) < 0;
+  const int flip = (steep != negx) ? (int)0x80000000 : 0;
+  const double sa = __hiloint2double(__double2hiint(a) ^ flip, __double2loint(a));
+  const double m = __hiloint2double(steep ? 0x3ff00000 : (negx ? 0x40000000 : 0), 0);
+  a = fma(m, kLeanAtan[15], fma(m, kLeanAtan[14], sa));
   return __hiloint2double((__double2hiint(a) & 0x7fffffff) | (__double2hiint(y) & 0x80000000),
                           __double2loint(a));
 }
