@@ -259,6 +259,9 @@ constexpr int kDpPUnroll = ACRO_DP_UNROLL;
 #ifndef ACRO_DP_FENCE
 #define ACRO_DP_FENCE 0
 #endif
+#ifndef ACRO_DP_WAR_FENCE
+#define ACRO_DP_WAR_FENCE 0
+#endif
 
 __device__ __forceinline__ void dp_cp_async_16(void* smem_dst, const void* gmem_src) {
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -267,6 +270,38 @@ __device__ __forceinline__ void dp_cp_async_16(void* smem_dst, const void* gmem_
 __device__ __forceinline__ void dp_cp_async_8(void* smem_dst, const void* gmem_src) {
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void dp_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void dp_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool dp_mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void dp_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          (unsigned)__cvta_generic_to_shared(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+      : "memory");
 }
 
 __device__ __forceinline__ double dp_ld_volatile(const double* p) {
@@ -307,27 +342,51 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
                          double* value, int32_t* __restrict__ pred, const DpWeights w,
                          unsigned* sync) {
   extern __shared__ __align__(16) unsigned char dp_smem[];
-  // rows padded to an odd number of doubles: lane j reads row j without bank conflicts (the
-  // evaluation is bound by these shared-memory reads: with a pitch of 6 doubles - 2-way
-  // conflicts - a layer takes 6200 cycles instead of 4800)
-  constexpr int kPitch = NDOF | 1;
+  // The rows of a layer lie in shared memory as they lie in global memory (pitch NDOF), so a
+  // layer arrives with ONE TMA bulk copy issued by one thread (round 2 first version: rows
+  // padded to an odd pitch and copied element-wise with 8-byte cp.async - 20 copies per thread
+  // and layer, 2 600 cycles of issue on the critical path of every transition).  Lane j reads
+  // row j: conflict free with 16-byte reads when NDOF is even (a 48-byte lane stride covers
+  // every bank once per quarter warp), with 8-byte reads when NDOF is odd.
+  constexpr int kPitch = NDOF;
   constexpr int kRowCap = kDpPMaxNodes * kPitch;     // doubles per row buffer
   double* s_q = reinterpret_cast<double*>(dp_smem);  // [2][kRowCap]
   double* s_v = s_q + 2 * kRowCap;                   // [kDpPMaxNodes]
+  __shared__ __align__(8) uint64_t s_bar[2];         // one mbarrier per row buffer
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
   unsigned* flag = sync + 1;
-  // asynchronous copy of a layer's joint rows into buffer `buf`
+  if (tid == 0) {
+    dp_mbar_init(&s_bar[0], 1);
+    dp_mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the rows of every layer go by bulk copy when source addresses and sizes are multiples of 16
+  // bytes: even NDOF and a 16-byte aligned q (one decision for the whole walk - the barrier
+  // phases below count one copy per layer)
+  const bool bulk = (NDOF % 2 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+  // asynchronous copy of a layer's joint rows into buffer `buf`.  The buffer was last read in
+  // the previous transition, which ended with __syncthreads.
   auto prefetch_rows = [&](int64_t layer, int buf) {
     const int64_t r0 = __ldg(offsets + layer);
     const int cnt = (int)(__ldg(offsets + layer + 1) - r0) * NDOF;  // doubles
     const double* src = q + r0 * NDOF;
     double* dst = s_q + buf * kRowCap;
-    for (int e = tid; e < cnt; e += kDpPThreads) {
-      const int r = e / NDOF, c = e - r * NDOF;
-      dp_cp_async_8(dst + r * kPitch + c, src + e);
+    if (bulk) {
+      if (tid == 0) {
+#if ACRO_DP_WAR_FENCE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        // (no proxy fence by default: the buffer's last generic-proxy accesses were reads,
+        // complete before the __syncthreads that ended the previous transition)
+        dp_mbar_expect_tx(&s_bar[buf], (unsigned)cnt * 8u);
+        dp_bulk_g2s(dst, src, (unsigned)cnt * 8u, &s_bar[buf]);
+      }
+    } else {
+      for (int e = tid; e < cnt; e += kDpPThreads) dp_cp_async_8(dst + e, src + e);
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");  // (empty after a bulk copy)
   };
   // the joint rows are read once, i.e. from DRAM: pull them into L2 two layers ahead
   auto prefetch_l2 = [&](int64_t layer) {
@@ -368,11 +427,53 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) tq0[i] = k_first < nd ? __ldg(q + (d0 + k_first) * NDOF + i) : 0.0;
     ACRO_DP_T(t_pre)
-    for (int j = tid; j < ns; j += kDpPThreads) s_v[j] = dp_wait_value(value + s0 + j, flag);
+    {
+      // every thread fetches all of its source values at once (one L2 round trip instead of one
+      // per value) and re-fetches, again all at once, those that had not been produced yet
+      constexpr int kPer = (kDpPMaxNodes + kDpPThreads - 1) / kDpPThreads;
+      double v[kPer];
+      unsigned pending = 0;
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int j = tid + u * kDpPThreads;
+        v[u] = j < ns ? dp_ld_volatile(value + s0 + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u)
+        if (!(v[u] == v[u])) pending |= 1u << u;
+      long long t0 = 0;
+      for (unsigned spins = 1; pending != 0u; ++spins) {
+#pragma unroll
+        for (int u = 0; u < kPer; ++u)
+          if ((pending >> u) & 1u) v[u] = dp_ld_volatile(value + s0 + tid + u * kDpPThreads);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u)
+          if (v[u] == v[u]) pending &= ~(1u << u);
+        if ((spins & 1023u) == 0u) {  // give up after ~2 s (sticky flag: nobody waits any more)
+          if (t0 == 0) t0 = clock64();
+          if (*reinterpret_cast<volatile unsigned*>(flag) != 0u) break;
+          if (clock64() - t0 > 4000000000LL) {
+            atomicExch(flag, 1u);
+            break;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int j = tid + u * kDpPThreads;
+        if (j < ns) s_v[j] = v[u];
+      }
+    }
     if (l + 1 < n_layers)
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     else
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (bulk) {
+      // rows of layer l - 1: the ((l - 1) >> 1)-th copy into buffer (l - 1) & 1
+      const unsigned parity = (unsigned)((l - 1) >> 1) & 1u;
+      while (!dp_mbar_try_wait(&s_bar[(l - 1) & 1], parity)) {
+      }
+    }
     __syncthreads();
     ACRO_DP_T(t_wait)
     for (int k = k_first; k < nd; k += G * kDpPWarps) {
@@ -392,9 +493,22 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
           const int j = j0 + 32 * u;
           const bool ok = j < ns;
           double acc = 0.0;
+          double sr[NDOF];
+          const double* rowp = sq + (ok ? j : 0) * kPitch;
+          if (NDOF % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < NDOF / 2; ++i) {
+              const double2 v2 = reinterpret_cast<const double2*>(rowp)[i];
+              sr[2 * i] = v2.x;
+              sr[2 * i + 1] = v2.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NDOF; ++i) sr[i] = rowp[i];
+          }
 #pragma unroll
           for (int i = 0; i < NDOF; ++i) {
-            const double d = (ok ? sq[j * kPitch + i] : tq[i]) - tq[i];
+            const double d = sr[i] - tq[i];
             if (COST == 0) acc += fabs(d);
             if (COST == 1 || COST == 2) acc = fma(d, d, acc);
             if (COST == 3) acc = fma(w.w[i] * d, d, acc);
@@ -450,7 +564,7 @@ static cudaError_t try_persistent(const double* q, int ndof, const int64_t* offs
   for (int64_t l = 0; l < n_layers; ++l)
     if (offsets_host[l + 1] - offsets_host[l] > kDpPMaxNodes) return cudaSuccess;
   // two row buffers + the source values
-  const size_t smem = sizeof(double) * ((size_t)2 * kDpPMaxNodes * (ndof | 1) + kDpPMaxNodes);
+  const size_t smem = sizeof(double) * ((size_t)2 * kDpPMaxNodes * ndof + kDpPMaxNodes);
   int dev = 0, sms = 0, coop = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
