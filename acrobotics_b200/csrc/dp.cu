@@ -253,6 +253,11 @@ constexpr int kDpPMaxNodes = 1920;  // two padded row buffers of 6-dof layers fi
 #define ACRO_DP_UNROLL 8
 #endif
 constexpr int kDpPUnroll = ACRO_DP_UNROLL;
+#ifndef ACRO_DP_BATCH
+#define ACRO_DP_BATCH 6
+#endif
+constexpr int kDpPBatch = ACRO_DP_BATCH;  // targets scored per pass over the source rows
+static_assert(kDpPBatch <= kDpPWarps, "one warp finishes one target of a batch");
 #ifndef ACRO_DP_TIMING
 #define ACRO_DP_TIMING 0
 #endif
@@ -329,6 +334,27 @@ __device__ __forceinline__ double dp_wait_value(const double* p, unsigned* flag)
   }
 }
 
+// Minimum of (value, index) pairs over the lanes of `mask` (lowest non-negative index among
+// equal values, -1 when nobody holds an index): the value through a monotone 64-bit key and two
+// 32-bit hardware reductions, the index through a third.  Values are never NaN here.
+__device__ __forceinline__ void dp_warp_argmin(unsigned mask, double& b, int& bj) {
+  const long long bits = __double_as_longlong(b);
+  // IEEE doubles order like sign-magnitude integers: flip all bits of negatives, the sign bit
+  // of non-negatives
+  const unsigned long long key =
+      (unsigned long long)bits ^ ((bits >> 63) | (long long)0x8000000000000000ULL);
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_min_sync(mask, hi);
+  const unsigned mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xffffffffu);
+  const bool mine = hi == mhi && lo == mlo;
+  const unsigned mj = __reduce_min_sync(mask, mine ? (unsigned)bj : 0xffffffffu);
+  const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+  const long long mbits =
+      (long long)(mkey ^ (((long long)~mkey >> 63) | (long long)0x8000000000000000ULL));
+  b = __longlong_as_double(mbits);
+  bj = (int)mj;
+}
+
 __device__ __forceinline__ bool dp_better(double ob, int oj, double b, int bj) {
   return ob < b || (ob == b && oj >= 0 && (bj < 0 || oj < bj));
 }
@@ -353,6 +379,8 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
   double* s_q = reinterpret_cast<double*>(dp_smem);  // [2][kRowCap]
   double* s_v = s_q + 2 * kRowCap;                   // [kDpPMaxNodes]
   __shared__ __align__(8) uint64_t s_bar[2];         // one mbarrier per row buffer
+  __shared__ double s_pb[kDpPBatch][kDpPWarps];      // per-warp partial minima of a batch
+  __shared__ int s_pj[kDpPBatch][kDpPWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
   unsigned* flag = sync + 1;
@@ -421,11 +449,21 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
     // this layer's rows are the source rows of the next transition: start copying them now
     if (l + 1 < n_layers) prefetch_rows(l, l & 1);
     prefetch_l2(l + 2);
-    // this warp's first target row (read-only input): in flight while the values arrive
-    const int k_first = blockIdx.x + G * warp;
-    double tq0[NDOF];
+    // The CTA owns the targets k = blockIdx.x + G t, t < tpc (6 of a layer of 840 nodes), and
+    // evaluates them kDpPBatch at a time: every thread takes a share of the SOURCE rows and
+    // scores each of its rows against all targets of the batch, so that a row is read from
+    // shared memory once per batch instead of once per target (with one warp per target the
+    // transition was bound by 6 x 40 KB of shared-memory reads, and two of the eight warps had
+    // nothing to do).  The first batch's target rows (read-only input, the same addresses for
+    // every thread) are in flight while the values arrive.
+    const int tpc = (nd + G - 1) / G;
+    double tq[kDpPBatch][NDOF];
 #pragma unroll
-    for (int i = 0; i < NDOF; ++i) tq0[i] = k_first < nd ? __ldg(q + (d0 + k_first) * NDOF + i) : 0.0;
+    for (int t = 0; t < kDpPBatch; ++t) {
+      const int k = blockIdx.x + G * t;
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) tq[t][i] = k < nd ? __ldg(q + (d0 + k) * NDOF + i) : 0.0;
+    }
     ACRO_DP_T(t_pre)
     {
       // every thread fetches all of its source values at once (one L2 round trip instead of one
@@ -476,69 +514,83 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
     }
     __syncthreads();
     ACRO_DP_T(t_wait)
-    for (int k = k_first; k < nd; k += G * kDpPWarps) {
-      double tq[NDOF];
+    for (int t0 = 0; t0 < tpc; t0 += kDpPBatch) {  // CTA-uniform trip count (one batch as a rule)
+      if (t0 > 0) {
 #pragma unroll
-      for (int i = 0; i < NDOF; ++i) tq[i] = k == k_first ? tq0[i] : __ldg(q + (d0 + k) * NDOF + i);
-      double best = 1.0 / 0.0;
-      int best_j = -1;
-      // kDpPUnroll independent source nodes per lane and step (the FP64 accumulation of one
-      // edge is a dependent chain - its order is part of the result - so the parallelism has to
-      // come from several edges in flight); ascending index within a lane and a strict
-      // comparison: the lowest index wins ties, like the per-layer kernels
-      for (int j0 = lane; j0 < ns; j0 += 32 * kDpPUnroll) {
-        double c2[kDpPUnroll];
+        for (int t = 0; t < kDpPBatch; ++t) {
+          const int k = blockIdx.x + G * (t0 + t);
 #pragma unroll
-        for (int u = 0; u < kDpPUnroll; ++u) {
-          const int j = j0 + 32 * u;
-          const bool ok = j < ns;
-          double acc = 0.0;
-          double sr[NDOF];
-          const double* rowp = sq + (ok ? j : 0) * kPitch;
-          if (NDOF % 2 == 0) {
+          for (int i = 0; i < NDOF; ++i) tq[t][i] = k < nd ? __ldg(q + (d0 + k) * NDOF + i) : 0.0;
+        }
+      }
+      double best[kDpPBatch];
+      int best_j[kDpPBatch];
 #pragma unroll
-            for (int i = 0; i < NDOF / 2; ++i) {
-              const double2 v2 = reinterpret_cast<const double2*>(rowp)[i];
-              sr[2 * i] = v2.x;
-              sr[2 * i + 1] = v2.y;
-            }
-          } else {
+      for (int t = 0; t < kDpPBatch; ++t) {
+        best[t] = 1.0 / 0.0;
+        best_j[t] = -1;
+      }
+      // ascending source index within a thread and a strict comparison: the lowest index wins
+      // ties, like the per-layer kernels.  The FP64 accumulation of one edge is a dependent
+      // chain (its order is part of the result); the kDpPBatch edges of a row are independent.
+      for (int j = tid; j < ns; j += kDpPThreads) {
+        double sr[NDOF];
+        const double* rowp = sq + j * kPitch;
+        if (NDOF % 2 == 0) {
 #pragma unroll
-            for (int i = 0; i < NDOF; ++i) sr[i] = rowp[i];
+          for (int i = 0; i < NDOF / 2; ++i) {
+            const double2 v2 = reinterpret_cast<const double2*>(rowp)[i];
+            sr[2 * i] = v2.x;
+            sr[2 * i + 1] = v2.y;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i) sr[i] = rowp[i];
+        }
+        const double sv = s_v[j];
+#pragma unroll
+        for (int t = 0; t < kDpPBatch; ++t) {
+          double acc = 0.0;
 #pragma unroll
           for (int i = 0; i < NDOF; ++i) {
-            const double d = sr[i] - tq[i];
+            const double d = sr[i] - tq[t][i];
             if (COST == 0) acc += fabs(d);
             if (COST == 1 || COST == 2) acc = fma(d, d, acc);
             if (COST == 3) acc = fma(w.w[i] * d, d, acc);
           }
           if (COST == 1) acc = sqrt(acc);
-          c2[u] = ok ? s_v[j] + acc : 1.0 / 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < kDpPUnroll; ++u)
-          if (c2[u] < best) {
-            best = c2[u];
-            best_j = j0 + 32 * u;
+          const double c = sv + acc;
+          if (c < best[t]) {
+            best[t] = c;
+            best_j[t] = j;
           }
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
-        if (dp_better(ob, oj, best, best_j)) {
-          best = ob;
-          best_j = oj;
         }
       }
+      // minimum over the warp, then over the CTA's warps through shared memory
+#pragma unroll
+      for (int t = 0; t < kDpPBatch; ++t) dp_warp_argmin(0xffffffffu, best[t], best_j[t]);
       if (lane == 0) {
-        pred[d0 + k] = best_j;
-        __stcg(value + d0 + k, best + (state_cost ? state_cost[d0 + k] : 0.0));
-#if ACRO_DP_FENCE
-        __threadfence();
-#endif
+#pragma unroll
+        for (int t = 0; t < kDpPBatch; ++t) {
+          s_pb[t][warp] = best[t];
+          s_pj[t][warp] = best_j[t];
+        }
       }
+      __syncthreads();
+      if (warp < kDpPBatch) {
+        const int k = blockIdx.x + G * (t0 + warp);
+        double b = lane < kDpPWarps ? s_pb[warp][lane] : 1.0 / 0.0;
+        int bj = lane < kDpPWarps ? s_pj[warp][lane] : -1;
+        dp_warp_argmin(0xffffffffu, b, bj);
+        if (lane == 0 && k < nd) {
+          pred[d0 + k] = bj;
+          __stcg(value + d0 + k, b + (state_cost ? state_cost[d0 + k] : 0.0));
+#if ACRO_DP_FENCE
+          __threadfence();
+#endif
+        }
+      }
+      if (t0 + kDpPBatch < tpc) __syncthreads();  // the partials are reused by the next batch
     }
     ACRO_DP_T(t_comp)
     __syncthreads();  // s_v and the row buffer of this transition are free again

@@ -235,3 +235,45 @@ def test_shortest_path_many_layers_single_launch(gpu, cost):
         assert _native.launch_count() - before == 2  # the persistent kernel + the backtrack
         assert got["success"] and abs(got["length"] - ref["length"]) <= 1e-9 * max(1, ref["length"])
         assert np.array_equal(np.array(got["path"]), np.array(ref["path"]))
+
+
+@pytest.mark.parametrize("ndof", [2, 3, 7])
+def test_shortest_path_single_launch_other_widths(gpu, ndof):
+    """The persistent kernel's two row-copy paths: one TMA bulk copy per layer when rows and
+    base are multiples of 16 bytes (even widths), element-wise cp.async otherwise (odd widths)."""
+    from acrobotics_b200 import _native
+    from acrobotics_b200.planning import shortest_path
+    from oracle import dp_oracle
+
+    rng = np.random.default_rng(30 + ndof)
+    sizes = list(rng.integers(1, 300, 40)) + [1900, 3, 700]
+    layers = [np.round(rng.uniform(-2, 2, (n, ndof)), 1) for n in sizes]
+    for cost in ("sum_squared", "norm_l1"):
+        ref = dp_oracle.shortest_path(layers, cost)
+        before = _native.launch_count()
+        got = shortest_path(layers, cost)
+        assert _native.launch_count() - before == 2
+        assert abs(got["length"] - ref["length"]) <= 1e-9 * max(1, ref["length"])
+        assert np.array_equal(np.array(got["path"]), np.array(ref["path"]))
+
+
+def test_shortest_path_single_launch_rows_not_16_byte_aligned(gpu):
+    """q rows that start 8 bytes off a 16-byte boundary take the element-wise copy path."""
+    import torch
+
+    from acrobotics_b200.planning import shortest_path_csr
+    from oracle import dp_oracle
+
+    rng = np.random.default_rng(41)
+    sizes = list(rng.integers(1, 200, 48))
+    layers = [np.round(rng.uniform(-2, 2, (n, 6)), 1) for n in sizes]
+    ref = dp_oracle.shortest_path(layers, "sum_squared")
+    q = np.concatenate(layers)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    flat = torch.zeros(q.size + 1, dtype=torch.float64, device="cuda")
+    flat[1:] = torch.as_tensor(q.ravel()).cuda()
+    qd = flat[1:].view(-1, 6)
+    assert qd.data_ptr() % 16 == 8
+    rows, length = shortest_path_csr(qd, offsets, "sum_squared")
+    assert abs(length - ref["length"]) <= 1e-9 * max(1, ref["length"])
+    assert np.array_equal(q[rows.cpu().numpy()], np.array(ref["path"]))
