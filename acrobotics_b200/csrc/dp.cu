@@ -246,7 +246,10 @@ __global__ void dp_backtrack_kernel(const double* __restrict__ value,
 // sticky flag, after which nobody waits any more - the kernel can not hang the device; the
 // back-tracking kernel then reports a NaN length.
 // ---------------------------------------------------------------------------
-constexpr int kDpPThreads = 256;
+#ifndef ACRO_DP_THREADS
+#define ACRO_DP_THREADS 256
+#endif
+constexpr int kDpPThreads = ACRO_DP_THREADS;
 constexpr int kDpPWarps = kDpPThreads / 32;
 constexpr int kDpPMaxNodes = 1920;  // two padded row buffers of 6-dof layers fit in 227 KB
 #ifndef ACRO_DP_UNROLL
