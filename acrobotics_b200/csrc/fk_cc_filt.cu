@@ -66,29 +66,44 @@ __device__ __forceinline__ void cp_async_wait() {
 //           ever decide a configuration - and everything after split_slot) with full lanes,
 //           and OR late verdicts into the mask words with atomics.
 // split_slot = 0 keeps the single pass (slot windows of filter_chunk).
-template <int NDOF, typename MaskT, bool PRISM, bool ROTID>
-__global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
+// CTA size.  Each warp needs ~8 KB of shared memory (prefetch buffers, stash, saved poses) and
+// each CTA another 3.3 KB (scene, half extents, the driver's 1 KB), so with 128-thread CTAs six
+// fit an SM (24 warps, although the 72-register build allows 28): fewer, larger CTAs amortise
+// the per-CTA part - 9 warps x 3 CTAs = 27 warps, 14 warps x 2 CTAs = 28 warps for Kuka against
+// a 16-box scene (+5.6 % throughput).  The launcher instantiates all three sizes and takes the
+// one with the most resident warps for the robot and scene at hand.
+#ifndef ACRO_K2_WARPS
+#define ACRO_K2_WARPS 0  // 0 = choose at launch; 4 / 9 / 14 = force (tuning)
+#endif
+typedef unsigned k2_stash_t;  // configuration indices below 2^32 (checked by the launcher)
+constexpr int k2_min_ctas(int warps) { return warps <= 4 ? 7 : (warps <= 9 ? 3 : 2); }
+
+template <int NDOF, typename MaskT, bool PRISM, bool ROTID, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, k2_min_ctas(WARPS))
     fk_cc_filter_kernel(const __grid_constant__ RobotDev<float> rb, const GridView grid,
                         const SceneView<float> sc, const int n_saved, const int split_slot,
                         const unsigned early_mask, const double* __restrict__ q, const int64_t n, const int layout,
                         uint32_t* __restrict__ mask, uint32_t* __restrict__ amb_mask,
                         unsigned long long* __restrict__ work_counter) {
-  // Shared memory.  Everything whose size is known at compile time is a STATIC array, so that its
-  // address is an immediate plus the warp / lane offset: with one dynamic block carved by hand
-  // the compiler, short of registers at six CTAs per SM, rematerialised the base pointers 19
-  // times per chunk (S2R + 8 uniform instructions each: 8 % of all issued instructions).  Only
-  // the saved poses of the self-collision partners (n_saved is a property of the robot) stay
-  // dynamic.  Kuka x 16 boxes: 35 KB per CTA.  (Keeping the joint rows of the stashed
+  constexpr int kK2Threads = WARPS * 32;
+  // Shared memory.  The small per-warp arrays are STATIC, so that their addresses are an
+  // immediate plus the warp / lane offset: with one dynamic block carved by hand the compiler,
+  // short of registers, rematerialised the base pointers 19 times per chunk (S2R + 8 uniform
+  // instructions each: 8 % of all issued instructions).  The prefetch buffers sit at a
+  // compile-time offset of the dynamic block (they would exceed the 48 KB static limit in a
+  // 14-warp CTA); the saved poses of the self-collision partners (n_saved is a property of
+  // the robot) follow them.  Kuka x 16 boxes: 8 KB per warp + 2.3 KB per CTA.  (Keeping the joint rows of the stashed
   // configurations in shared memory instead of re-reading them from L2 in pass 2 drops
   // residency by one CTA per SM and was measured 9 % slower.)
-  constexpr int kWarps = kFThreads / 32;
+  constexpr int kWarps = WARPS;
   constexpr int kSceneCap = sizeof(MaskT) == 4 ? 32 : kMaxScene;  // a 32-bit mask means <= 32 boxes
-  __shared__ __align__(16) double s_q_all[kWarps][2 * 32 * NDOF];  // prefetch double buffer per warp
-  __shared__ long long s_stash_all[kWarps][64];
+  __shared__ k2_stash_t s_stash_all[kWarps][64];
   __shared__ __align__(16) float s_scene_st[kSceneCap * kSceneStrideF];
   __shared__ float s_half_st[kMaxSaved * 4];
   __shared__ uint16_t s_list_all[kWarps][kItemCap];
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // [kWarps][n_saved][12 * 32] floats
+  // dynamic: [kWarps][2 * 32 * NDOF] doubles (prefetch double buffer per warp, at a compile-time
+  // offset from the block's base), then [kWarps][n_saved][12 * 32] floats
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int t = threadIdx.x;
 #if ACRO_FILTER_PIN_IDS
   // opaque to the optimiser: keeps the lane / warp index in a register instead of re-reading
@@ -101,11 +116,11 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   const unsigned lane = t & 31;
   const int warp = t >> 5;
 #endif
-  for (int k = t; k < sc.n * kSceneStrideF; k += kFThreads) {
+  for (int k = t; k < sc.n * kSceneStrideF; k += kK2Threads) {
     const int j = k >> 4, e = k & 15;
     s_scene_st[k] = sc.boxes[j * kSceneStride + kScenePerm[e]];
   }
-  for (int b = t; b < rb.n_boxes; b += kFThreads) {
+  for (int b = t; b < rb.n_boxes; b += kK2Threads) {
     const int sl = rb.boxes[b].save_slot;
     if (sl >= 0) {
       s_half_st[4 * sl + 0] = rb.boxes[b].half[0];
@@ -118,11 +133,12 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
   ctx.s_scene = s_scene_st;
   ctx.s_half = s_half_st;
   ctx.list = s_list_all[warp];
-  ctx.s_saved = reinterpret_cast<float*>(smem_raw) + warp * n_saved * 12 * 32;
+  ctx.s_saved = reinterpret_cast<float*>(smem_raw + sizeof(double) * kWarps * 2 * 32 * NDOF) +
+                warp * n_saved * 12 * 32;
   ctx.extra = nullptr;
   ctx.n_scene = sc.n;
-  double* s_q = s_q_all[warp];
-  long long* s_stash = s_stash_all[warp];
+  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * (2 * 32 * NDOF);
+  k2_stash_t* s_stash = s_stash_all[warp];
   __syncthreads();
 
   const int64_t n_chunks = (n + 31) >> 5;
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(kFThreads, ACRO_FILTER_MIN_CTAS)
         // undecided and unambiguous configurations continue in pass 2
         const bool cont = act && !retired && !amb;
         const unsigned cm = __ballot_sync(kFull, cont);
-        if (cont) s_stash[stashed + __popc(cm & ((1u << lane) - 1u))] = (long long)idx;
+        if (cont) s_stash[stashed + __popc(cm & ((1u << lane) - 1u))] = (k2_stash_t)idx;
         stashed += __popc(cm);
       }
 #if ACRO_FILTER_DYNAMIC
@@ -395,22 +411,27 @@ size_t filter_scratch_bytes(int64_t n) {
   return ((words * sizeof(uint32_t) + 7) / 8) * 8 + 8;
 }
 
-size_t filter_smem_bytes(int ndof, int n_scene, int n_saved) {
-  // the dynamic part only: the saved poses of the self-collision partners (the rest is static)
-  (void)ndof;
+size_t filter_smem_bytes(int ndof, int n_scene, int n_saved, int warps) {
+  // the dynamic part: the prefetch buffers and the saved poses of the self-collision partners
   (void)n_scene;
-  return sizeof(float) * (kFThreads / 32) * (size_t)n_saved * 12 * 32;
+  return (size_t)warps *
+         (sizeof(double) * 2 * 32 * ndof + sizeof(float) * (size_t)n_saved * 12 * 32);
 }
 
-// resident CTAs of the persistent filter kernel on the current device
+// resident CTAs per SM of a filter kernel instantiation with `smem` dynamic bytes (0: does not fit)
 template <typename K>
-static int persistent_blocks(K kern, size_t smem) {
-  int dev = 0, sms = 0, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  return sms * per_sm;
+static int resident_ctas(K kern, int threads, size_t smem) {
+  int per_sm = 0;
+  if (smem > 24 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return per_sm;
 }
 
 cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,
@@ -427,7 +448,7 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
     cudaError_t e0 = cudaMemsetAsync(work_counter, 0, 8, st);
     if (e0 != cudaSuccess) return e0;
   }
-  const int64_t tiles = (n + kFThreads - 1) / kFThreads;
+  if (n > 0xffffffffLL) return cudaErrorInvalidValue;  // stash entries are 32-bit indices
   int n_saved = 0;
   for (int b = 0; b < rb32.n_boxes; ++b)
     if (rb32.boxes[b].save_slot + 1 > n_saved) n_saved = rb32.boxes[b].save_slot + 1;
@@ -437,37 +458,56 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
   // pass 2 unless the split is so early that nothing else is left for pass 1
   unsigned early_mask = split_slot > 0 ? ((2u << split_slot) - 1u) : ~0u;
   if (split_slot >= 2) early_mask &= ~3u;
+  int sms = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const bool prism = rb32.prismatic_mask != 0;
+  bool rotid = !prism;  // the specialised instantiation exists for all-revolute chains
+  for (int b = 0; b < rb32.n_boxes; ++b) rotid = rotid && rb32.boxes[b].rot_identity != 0;
+#define ACRO_K2_PICK(M, P, R)                                                             \
+  pick(fk_cc_filter_kernel<NDOF, M, P, R, 4>, fk_cc_filter_kernel<NDOF, M, P, R, 9>,      \
+       fk_cc_filter_kernel<NDOF, M, P, R, 14>)
   ACRO_DISPATCH_NDOF(rb32.ndof, {
-    const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved);
-    auto launch = [&](auto kern) -> cudaError_t {
-      // static (<= 24 KB) + dynamic shared memory beyond 48 KB needs the opt-in
-      if (smem > 24 * 1024) {
-        cudaError_t e2 =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e2 != cudaSuccess) return e2;
-      }
-      const int64_t blocks = std::min<int64_t>(tiles, persistent_blocks(kern, smem));
-      kern<<<(unsigned)blocks, kFThreads, smem, st>>>(rb32, grid, sc32, n_saved, split_slot,
-                                                      early_mask, q, n, layout, mask, amb_mask,
-                                                      work_counter);
-      return cudaSuccess;
+    // one CTA size: resident CTAs per SM (0 = does not fit), launch
+    auto resident = [&](auto kern, int warps) {
+      return resident_ctas(kern, warps * 32, filter_smem_bytes(NDOF, sc32.n, n_saved, warps));
     };
-    const bool prism = rb32.prismatic_mask != 0;
-    bool rotid = !prism;  // the specialised instantiation exists for all-revolute chains
-    for (int b = 0; b < rb32.n_boxes; ++b) rotid = rotid && rb32.boxes[b].rot_identity != 0;
+    auto launch = [&](auto kern, int warps, int per_sm) -> cudaError_t {
+      const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved, warps);
+      const int64_t tiles = (n + warps * 32 - 1) / (warps * 32);
+      const int64_t blocks = std::min<int64_t>(tiles, (int64_t)sms * per_sm);
+      kern<<<(unsigned)blocks, warps * 32, smem, st>>>(rb32, grid, sc32, n_saved, split_slot,
+                                                       early_mask, q, n, layout, mask, amb_mask,
+                                                       work_counter);
+      return cudaGetLastError();
+    };
+    // the CTA size with the most resident warps (ties: the smaller CTA)
+    auto pick = [&](auto k4, auto k9, auto k14) -> cudaError_t {
+      const int forced = ACRO_K2_WARPS;
+      const int r4 = (forced == 0 || forced == 4) ? resident(k4, 4) : 0;
+      const int r9 = (forced == 0 || forced == 9) ? resident(k9, 9) : 0;
+      const int r14 = (forced == 0 || forced == 14) ? resident(k14, 14) : 0;
+      const int w4 = 4 * r4, w9 = 9 * r9, w14 = 14 * r14;
+      if (w4 == 0 && w9 == 0 && w14 == 0) return cudaErrorInvalidConfiguration;
+      if (w14 > w9 && w14 > w4) return launch(k14, 14, r14);
+      if (w9 > w4) return launch(k9, 9, r9);
+      return launch(k4, 4, r4);
+    };
     if (mask_bits == 32)
-      e = prism   ? launch(fk_cc_filter_kernel<NDOF, uint32_t, true, false>)
-          : rotid ? launch(fk_cc_filter_kernel<NDOF, uint32_t, false, true>)
-                  : launch(fk_cc_filter_kernel<NDOF, uint32_t, false, false>);
+      e = prism   ? ACRO_K2_PICK(uint32_t, true, false)
+          : rotid ? ACRO_K2_PICK(uint32_t, false, true)
+                  : ACRO_K2_PICK(uint32_t, false, false);
     else
-      e = prism   ? launch(fk_cc_filter_kernel<NDOF, uint64_t, true, false>)
-          : rotid ? launch(fk_cc_filter_kernel<NDOF, uint64_t, false, true>)
-                  : launch(fk_cc_filter_kernel<NDOF, uint64_t, false, false>);
+      e = prism   ? ACRO_K2_PICK(uint64_t, true, false)
+          : rotid ? ACRO_K2_PICK(uint64_t, false, true)
+                  : ACRO_K2_PICK(uint64_t, false, false);
     if (e != cudaSuccess) return e;
     count_launch();
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
   });
+#undef ACRO_K2_PICK
   if (e != cudaSuccess) return e;
   return launch_fk_cc_fixup(rb64, sc64, q, n, layout, mask, amb_mask, near_mask, margin, st);
 }
