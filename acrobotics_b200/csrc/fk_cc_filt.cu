@@ -77,6 +77,11 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 typedef unsigned k2_stash_t;  // configuration indices below 2^32 (checked by the launcher)
 constexpr int k2_min_ctas(int warps) { return warps <= 4 ? 7 : (warps <= 9 ? 3 : 2); }
+// do the per-warp static arrays (prefetch buffers, stash, list) fit the 48 KB static limit?
+__host__ __device__ constexpr bool k2_static_q(int ndof, int warps) {
+  return (size_t)warps * (sizeof(double) * 2 * 32 * ndof + sizeof(k2_stash_t) * 64 +
+                          sizeof(uint16_t) * kItemCap) <= 48 * 1024;
+}
 
 template <int NDOF, typename MaskT, bool PRISM, bool ROTID, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, k2_min_ctas(WARPS))
@@ -97,13 +102,20 @@ __global__ void __launch_bounds__(WARPS * 32, k2_min_ctas(WARPS))
   // residency by one CTA per SM and was measured 9 % slower.)
   constexpr int kWarps = WARPS;
   constexpr int kSceneCap = sizeof(MaskT) == 4 ? 32 : kMaxScene;  // a 32-bit mask means <= 32 boxes
+  // static while it fits the 48 KB static limit: the per-warp prefetch double buffers, stashes
+  // and candidate lists (14 warps x 3 456 B for six joints).  Dynamic, in this order: the
+  // half extents of the saved slots and the scene (CTA wide, at compile-time offsets), the
+  // prefetch buffers when they did not fit above, the saved poses of the self-collision
+  // partners ([kWarps][n_saved][12 * 32] floats).
+  constexpr bool kStaticQ = k2_static_q(NDOF, WARPS);
+  __shared__ __align__(16) double s_q_all[kStaticQ ? kWarps : 1][kStaticQ ? 2 * 32 * NDOF : 2];
   __shared__ k2_stash_t s_stash_all[kWarps][64];
-  __shared__ __align__(16) float s_scene_st[kSceneCap * kSceneStrideF];
-  __shared__ float s_half_st[kMaxSaved * 4];
   __shared__ uint16_t s_list_all[kWarps][kItemCap];
-  // dynamic: [kWarps][2 * 32 * NDOF] doubles (prefetch double buffer per warp, at a compile-time
-  // offset from the block's base), then [kWarps][n_saved][12 * 32] floats
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_half_st = reinterpret_cast<float*>(smem_raw);
+  float* s_scene_st = s_half_st + kMaxSaved * 4;
+  constexpr size_t kDynQ = sizeof(float) * (kMaxSaved * 4 + kSceneCap * kSceneStrideF);
+  constexpr size_t kDynSaved = kDynQ + (kStaticQ ? 0 : sizeof(double) * kWarps * 2 * 32 * NDOF);
   const int t = threadIdx.x;
 #if ACRO_FILTER_PIN_IDS
   // opaque to the optimiser: keeps the lane / warp index in a register instead of re-reading
@@ -133,11 +145,11 @@ __global__ void __launch_bounds__(WARPS * 32, k2_min_ctas(WARPS))
   ctx.s_scene = s_scene_st;
   ctx.s_half = s_half_st;
   ctx.list = s_list_all[warp];
-  ctx.s_saved = reinterpret_cast<float*>(smem_raw + sizeof(double) * kWarps * 2 * 32 * NDOF) +
-                warp * n_saved * 12 * 32;
+  ctx.s_saved = reinterpret_cast<float*>(smem_raw + kDynSaved) + warp * n_saved * 12 * 32;
   ctx.extra = nullptr;
   ctx.n_scene = sc.n;
-  double* s_q = reinterpret_cast<double*>(smem_raw) + warp * (2 * 32 * NDOF);
+  double* s_q = kStaticQ ? s_q_all[kStaticQ ? warp : 0]
+                         : reinterpret_cast<double*>(smem_raw + kDynQ) + warp * (2 * 32 * NDOF);
   k2_stash_t* s_stash = s_stash_all[warp];
   __syncthreads();
 
@@ -411,19 +423,22 @@ size_t filter_scratch_bytes(int64_t n) {
   return ((words * sizeof(uint32_t) + 7) / 8) * 8 + 8;
 }
 
-size_t filter_smem_bytes(int ndof, int n_scene, int n_saved, int warps) {
-  // the dynamic part: the prefetch buffers and the saved poses of the self-collision partners
-  (void)n_scene;
-  return (size_t)warps *
-         (sizeof(double) * 2 * 32 * ndof + sizeof(float) * (size_t)n_saved * 12 * 32);
+size_t filter_smem_bytes(int ndof, int mask_bits, int n_saved, int warps) {
+  // the dynamic part: half extents of the saved slots, the scene, the prefetch buffers when
+  // they do not fit the static limit, the saved poses of the self-collision partners
+  const int scene_cap = mask_bits == 32 ? 32 : kMaxScene;
+  return sizeof(float) * (kMaxSaved * 4 + (size_t)scene_cap * kSceneStrideF) +
+         (k2_static_q(ndof, warps) ? 0 : (size_t)warps * sizeof(double) * 2 * 32 * ndof) +
+         (size_t)warps * sizeof(float) * (size_t)n_saved * 12 * 32;
 }
 
 // resident CTAs per SM of a filter kernel instantiation with `smem` dynamic bytes (0: does not fit)
 template <typename K>
 static int resident_ctas(K kern, int threads, size_t smem) {
   int per_sm = 0;
-  if (smem > 24 * 1024 &&
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  // static + dynamic shared memory beyond 48 KB needs the opt-in (the static part alone is 47 KB
+  // in the 14-warp instantiation)
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -473,10 +488,10 @@ cudaError_t launch_fk_cc_filter(const RobotDev<float>& rb32, const RobotDev<doub
   ACRO_DISPATCH_NDOF(rb32.ndof, {
     // one CTA size: resident CTAs per SM (0 = does not fit), launch
     auto resident = [&](auto kern, int warps) {
-      return resident_ctas(kern, warps * 32, filter_smem_bytes(NDOF, sc32.n, n_saved, warps));
+      return resident_ctas(kern, warps * 32, filter_smem_bytes(NDOF, mask_bits, n_saved, warps));
     };
     auto launch = [&](auto kern, int warps, int per_sm) -> cudaError_t {
-      const size_t smem = filter_smem_bytes(NDOF, sc32.n, n_saved, warps);
+      const size_t smem = filter_smem_bytes(NDOF, mask_bits, n_saved, warps);
       const int64_t tiles = (n + warps * 32 - 1) / (warps * 32);
       const int64_t blocks = std::min<int64_t>(tiles, (int64_t)sms * per_sm);
       kern<<<(unsigned)blocks, warps * 32, smem, st>>>(rb32, grid, sc32, n_saved, split_slot,
