@@ -155,7 +155,8 @@ int acro_fk_rpy_f64(const AcroRobot* robot, const double* q, int64_t n, int32_t 
  * each box pair decided by FCL's boxBox2 separating-axis test (shapes.py:50-58).
  * scene may be NULL (self collision only: Robot.is_in_self_collision,
  * robot.py:239-242).  near_mask (nullable): bit set when the configuration's
- * decisive SAT quantity is within +-margin of contact (reported separately).   */
+ * decisive SAT quantity is within +-margin of contact (reported separately).
+ * n < 2^32 per call (larger batches: several calls over row ranges).           */
 int acro_fk_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q, int64_t n,
                    int32_t q_layout, uint32_t* mask, uint32_t* near_mask, double margin,
                    void* stream);
