@@ -173,6 +173,22 @@ int build_dev(const AcroRobotDesc& d, RobotDev<real>& o) {
     for (int lo : partners[b]) o.partner[cursor++] = (uint8_t)lo;
   }
   for (int b = d.n_boxes; b <= kMaxBoxes; ++b) o.pair_begin[b] = (uint8_t)cursor;
+  // compact per-box records of the FP32 filter
+  for (int k = 0; k < cursor; ++k) o.partner_slot[k] = (uint8_t)o.boxes[o.partner[k]].save_slot;
+  for (int s = 0; s <= n + 1; ++s) {
+    for (int b = o.slot_begin[s]; b < o.slot_begin[s + 1]; ++b) {
+      const BoxDev<real>& bx = o.boxes[b];
+      BoxHot& h = o.hot[b];
+      h.off[0] = (float)bx.off[3];
+      h.off[1] = (float)bx.off[7];
+      h.off[2] = (float)bx.off[11];
+      h.radius = (float)bx.radius;
+      for (int e = 0; e < 3; ++e) h.half[e] = (float)bx.half[e];
+      h.meta = (uint32_t)s | ((uint32_t)bx.cull_class << 4) | ((uint32_t)(bx.save_slot + 1) << 9) |
+               ((uint32_t)(bx.rot_identity != 0) << 14) | ((uint32_t)o.pair_begin[b] << 16) |
+               ((uint32_t)(o.pair_begin[b + 1] - o.pair_begin[b]) << 24);
+    }
+  }
   return 0;
 }
 

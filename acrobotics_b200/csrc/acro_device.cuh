@@ -39,6 +39,16 @@ struct BoxDev {
   int32_t reserved;
 };
 
+// What the FP32 filter reads per robot box, packed into 32 bytes (two 16-byte constant loads
+// per box instead of a dozen scalar ones; always floats).  meta: bits 0-3 slot, 4-8 cull_class,
+// 9-13 save_slot + 1, 14 rot_identity, 16-23 first self pair, 24-31 number of self pairs.
+struct alignas(16) BoxHot {
+  float off[3];  // translation of the box in its carrier frame
+  float radius;
+  float half[3];
+  uint32_t meta;
+};
+
 template <typename real>
 struct RobotDev {
   int32_t ndof;
@@ -58,6 +68,9 @@ struct RobotDev {
   // partner[pair_begin[b] .. pair_begin[b+1]) and hold the earlier box index
   uint8_t pair_begin[kMaxBoxes + 1];
   uint8_t partner[kMaxPairs];
+  // the filter's view of the same data (see BoxHot); partner_slot[k] = save_slot of partner[k]
+  BoxHot hot[kMaxBoxes];
+  uint8_t partner_slot[kMaxPairs];
 };
 
 // Scene box, packed as kSceneStride reals:

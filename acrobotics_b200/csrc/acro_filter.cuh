@@ -330,39 +330,43 @@ amb = false;
       }
     }
     for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
-      const BoxDev<float>& bx = rb.boxes[b];
+      // everything the filter needs of the box: its 32-byte BoxHot record (two constant loads)
+      const float4 h0 = *reinterpret_cast<const float4*>(&rb.hot[b].off[0]);
+      const float4 h1 = *reinterpret_cast<const float4*>(&rb.hot[b].half[0]);
+      const unsigned meta = __float_as_uint(h1.w);
+      const float box_radius = h0.w;
       float Rw_copy[9], cw[3];
       const float* Rw = ROTID ? T.r : Rw_copy;
-      if (ROTID || bx.rot_identity) {
+      if (ROTID || ((meta >> 14) & 1u)) {
         if (!ROTID) {
 #pragma unroll
           for (int k = 0; k < 9; ++k) Rw_copy[k] = T.r[k];
         }
 #if ACRO_F32X2
         {  // rows 0 and 1 as one packed lane pair (the pairing of tf_mul_dh), row 2 scalar
-          const float2 c01 = fma2(bx.off[11], make_float2(T.r[2], T.r[5]),
-                                  fma2(bx.off[7], make_float2(T.r[1], T.r[4]),
-                                       fma2(bx.off[3], make_float2(T.r[0], T.r[3]),
+          const float2 c01 = fma2(h0.z, make_float2(T.r[2], T.r[5]),
+                                  fma2(h0.y, make_float2(T.r[1], T.r[4]),
+                                       fma2(h0.x, make_float2(T.r[0], T.r[3]),
                                             make_float2(T.p[0], T.p[1]))));
           cw[0] = c01.x;
           cw[1] = c01.y;
-          cw[2] = fmaf(T.r[8], bx.off[11], fmaf(T.r[7], bx.off[7], fmaf(T.r[6], bx.off[3], T.p[2])));
+          cw[2] = fmaf(T.r[8], h0.z, fmaf(T.r[7], h0.y, fmaf(T.r[6], h0.x, T.p[2])));
         }
 #else
 #pragma unroll
         for (int r = 0; r < 3; ++r)
-          cw[r] = fmaf(T.r[3 * r + 2], bx.off[11],
-                       fmaf(T.r[3 * r + 1], bx.off[7], fmaf(T.r[3 * r], bx.off[3], T.p[r])));
+          cw[r] = fmaf(T.r[3 * r + 2], h0.z,
+                       fmaf(T.r[3 * r + 1], h0.y, fmaf(T.r[3 * r], h0.x, T.p[r])));
 #endif
       } else {
         Tf<float> W;
-        tf_mul<float>(W, T, bx.off);
+        tf_mul<float>(W, T, rb.boxes[b].off);
 #pragma unroll
         for (int k = 0; k < 9; ++k) Rw_copy[k] = W.r[k];
 #pragma unroll
         for (int r = 0; r < 3; ++r) cw[r] = W.p[r];
       }
-      const float A0 = bx.half[0], A1 = bx.half[1], A2 = bx.half[2];
+      const float A0 = h1.x, A1 = h1.y, A2 = h1.z;
 
       // ---- candidates: scene boxes from the grid, self partners from a padded cull
       MaskT ms = 0;
@@ -376,22 +380,23 @@ amb = false;
           const unsigned dim = (unsigned)grid.dim;
           if ((unsigned)ix < dim && (unsigned)iy < dim && (unsigned)iz < dim) {
             // < 2^32 cells by construction (24 classes x 160^3)
-            const unsigned cell = (((unsigned)bx.cull_class * dim + iz) * dim + iy) * dim + ix;
+            const unsigned cell = ((((meta >> 4) & 31u) * dim + iz) * dim + iy) * dim + ix;
             ms = __ldg(reinterpret_cast<const MaskT*>(grid.cells) + cell);
           } else {
             ms = n_scene >= (int)(8 * sizeof(MaskT)) ? ~MaskT(0) : ((MaskT(1) << n_scene) - 1);
           }
         }
         if (do_self) {
-          for (int k = rb.pair_begin[b]; k < rb.pair_begin[b + 1]; ++k) {
-            const int sl = rb.boxes[rb.partner[k]].save_slot;
+          const int pair0 = (meta >> 16) & 255u, pair1 = pair0 + (int)(meta >> 24);
+          for (int k = pair0; k < pair1; ++k) {
+            const int sl = rb.partner_slot[k];
             // saved pose of the partner: 12 floats per lane as three 16-byte pieces (a lane
             // stride of 48 bytes is conflict free for 16-byte accesses)
             const float4* sv = reinterpret_cast<const float4*>(s_saved) + (sl * 32 + (int)lane) * 3;
             const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];  // R0 R3 R1 R4 | R2 R5 c0 c1 | R6 R7 R8 c2
             // partner's face axes against this box's bounding sphere, padded
             const float d0 = cw[0] - s1.z, d1 = cw[1] - s1.w, d2 = cw[2] - s2.w;
-            const float ra = bx.radius + delta;
+            const float ra = box_radius + delta;
             const float y0 = fmaf(s2.x, d2, fmaf(s0.y, d1, s0.x * d0));
             const float y1 = fmaf(s2.y, d2, fmaf(s0.w, d1, s0.z * d0));
             const float y2 = fmaf(s2.z, d2, fmaf(s1.y, d1, s1.x * d0));
@@ -446,7 +451,7 @@ amb = false;
             }
             float R2[9], T2[3], B0, B1, B2, rB;
             load_other(other, (int)lane, R2, T2, B0, B1, B2, rB);
-            const int res = sat_filter(A0, A1, A2, Rw, cw, R2, T2, B0, B1, B2, delta, bx.radius, rB);
+            const int res = sat_filter(A0, A1, A2, Rw, cw, R2, T2, B0, B1, B2, delta, box_radius, rB);
             if (res == kHit) {
               hit = true;
               done = true;
@@ -495,7 +500,7 @@ amb = false;
           if (valid && !owner_done) {
             float R2[9], T2[3], B0, B1, B2, rB;
             load_other(other, owner, R2, T2, B0, B1, B2, rB);
-            res = sat_filter(A0, A1, A2, R1, c1, R2, T2, B0, B1, B2, delta, bx.radius, rB);
+            res = sat_filter(A0, A1, A2, R1, c1, R2, T2, B0, B1, B2, delta, box_radius, rB);
           }
           const unsigned hb = __reduce_or_sync(kFull, res == kHit ? (1u << owner) : 0u);
           const unsigned ab = __reduce_or_sync(kFull, res == kAmb ? (1u << owner) : 0u);
@@ -508,10 +513,11 @@ amb = false;
         __syncwarp();
       }
 
-      if (do_self && bx.save_slot >= 0) {
+      const int save_slot = (int)((meta >> 9) & 31u) - 1;
+      if (do_self && save_slot >= 0) {
         // order: (R0,R3) (R1,R4) (R2,R5) (c0,c1) (R6,R7) (R8,c2) - the register pairs the packed
         // DH step and pose leave behind, stored as they are
-        float2* sv = reinterpret_cast<float2*>(s_saved) + (bx.save_slot * 32 + (int)lane) * 6;
+        float2* sv = reinterpret_cast<float2*>(s_saved) + (save_slot * 32 + (int)lane) * 6;
         sv[0] = make_float2(Rw[0], Rw[3]);
         sv[1] = make_float2(Rw[1], Rw[4]);
         sv[2] = make_float2(Rw[2], Rw[5]);
