@@ -173,6 +173,8 @@ int build_dev(const AcroRobotDesc& d, RobotDev<real>& o) {
     for (int lo : partners[b]) o.partner[cursor++] = (uint8_t)lo;
   }
   for (int b = d.n_boxes; b <= kMaxBoxes; ++b) o.pair_begin[b] = (uint8_t)cursor;
+  for (int i = 0; i < n; ++i)
+    o.dh4[i] = make_float4((float)o.ca[i], (float)o.sa[i], (float)o.a[i], (float)o.d[i]);
   // compact per-box records of the FP32 filter
   for (int k = 0; k < cursor; ++k) o.partner_slot[k] = (uint8_t)o.boxes[o.partner[k]].save_slot;
   for (int s = 0; s <= n + 1; ++s) {

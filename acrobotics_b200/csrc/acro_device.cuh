@@ -71,6 +71,8 @@ struct RobotDev {
   // the filter's view of the same data (see BoxHot); partner_slot[k] = save_slot of partner[k]
   BoxHot hot[kMaxBoxes];
   uint8_t partner_slot[kMaxPairs];
+  // (cos alpha, sin alpha, a, d) of every joint as one 16-byte constant load (floats)
+  float4 dh4[kMaxDof];
 };
 
 // Scene box, packed as kSceneStride reals:

@@ -321,12 +321,13 @@ amb = false;
         qi = 0.0;
       }
       float s, c;
+      const float4 dh = rb.dh4[i];  // (cos alpha, sin alpha, a, d)
       if (PRISM) {
         sincos_filter(prismatic ? (double)rb.theta[i] : qi, s, c);
-        tf_mul_dh<float>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], prismatic ? (float)qi : rb.d[i]);
+        tf_mul_dh<float>(T, c, s, dh.x, dh.y, dh.z, prismatic ? (float)qi : dh.w);
       } else {
         sincos_filter(qi, s, c);
-        tf_mul_dh<float>(T, c, s, rb.ca[i], rb.sa[i], rb.a[i], rb.d[i]);
+        tf_mul_dh<float>(T, c, s, dh.x, dh.y, dh.z, dh.w);
       }
     }
     for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
