@@ -399,8 +399,9 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
   const bool bulk = (NDOF % 2 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
   // asynchronous copy of a layer's joint rows into buffer `buf`.  The buffer was last read in
   // the previous transition, which ended with __syncthreads.
-  auto prefetch_rows = [&](int64_t r0, int64_t r1, int buf) {  // rows [r0, r1) of q
-    const int cnt = (int)(r1 - r0) * NDOF;  // doubles
+  auto prefetch_rows = [&](int64_t layer, int buf) {
+    const int64_t r0 = __ldg(offsets + layer);
+    const int cnt = (int)(__ldg(offsets + layer + 1) - r0) * NDOF;  // doubles
     const double* src = q + r0 * NDOF;
     double* dst = s_q + buf * kRowCap;
     if (bulk) {
@@ -419,22 +420,19 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
     asm volatile("cp.async.commit_group;\n" ::: "memory");  // (empty after a bulk copy)
   };
   // the joint rows are read once, i.e. from DRAM: pull them into L2 two layers ahead
-  auto prefetch_l2 = [&](int64_t r0, int64_t r1) {  // rows [r0, r1) of q (empty: nothing)
-    const int64_t bytes = (r1 - r0) * NDOF * (int64_t)sizeof(double);
+  auto prefetch_l2 = [&](int64_t layer) {
+    if (layer >= n_layers) return;
+    const int64_t r0 = __ldg(offsets + layer);
+    const int64_t bytes = (__ldg(offsets + layer + 1) - r0) * NDOF * (int64_t)sizeof(double);
     const char* src = reinterpret_cast<const char*>(q + r0 * NDOF);
     for (int64_t b = (int64_t)tid * 128; b < bytes; b += (int64_t)kDpPThreads * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
   };
-  // a sliding window of layer offsets o[k] = offsets[min(l - 1 + k, n_layers)] lives in
-  // registers; one new offset is fetched per transition, a whole transition before its use
-  // (the dependent offset loads were on the critical path of every layer)
-  auto off_at = [&](int64_t i) { return __ldg(offsets + (i < n_layers ? i : n_layers)); };
-  int64_t o0 = off_at(0), o1 = off_at(1), o2 = off_at(2), o3 = off_at(3), o4 = off_at(4);
-  prefetch_l2(o1, o2);
-  prefetch_l2(o2, o3);
-  prefetch_rows(o0, o1, 0);
+  prefetch_l2(1);
+  prefetch_l2(2);
+  prefetch_rows(0, 0);
   {
-    const int64_t n0 = o1 - o0;
+    const int64_t n0 = __ldg(offsets + 1) - __ldg(offsets);
     for (int64_t i = (int64_t)blockIdx.x * kDpPThreads + tid; i < n0; i += (int64_t)G * kDpPThreads) {
       pred[i] = -1;
       __stcg(value + i, state_cost ? state_cost[i] : 0.0);
@@ -448,13 +446,12 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
 #define ACRO_DP_T(acc)
 #endif
   for (int64_t l = 1; l < n_layers; ++l) {
-    const int64_t s0 = o0, d0 = o1;
-    const int ns = (int)(d0 - s0), nd = (int)(o2 - d0);
-    const int64_t o5 = off_at(l + 4);  // next transition's o4
+    const int64_t s0 = __ldg(offsets + l - 1), d0 = __ldg(offsets + l);
+    const int ns = (int)(d0 - s0), nd = (int)(__ldg(offsets + l + 1) - d0);
     const double* sq = s_q + ((l - 1) & 1) * kRowCap;
     // this layer's rows are the source rows of the next transition: start copying them now
-    if (l + 1 < n_layers) prefetch_rows(o1, o2, l & 1);
-    prefetch_l2(o3, o4);  // layer l + 2 (empty behind the last layer)
+    if (l + 1 < n_layers) prefetch_rows(l, l & 1);
+    prefetch_l2(l + 2);
     // The CTA owns the targets k = blockIdx.x + G t, t < tpc (6 of a layer of 840 nodes), and
     // evaluates them kDpPBatch at a time: every thread takes a share of the SOURCE rows and
     // scores each of its rows against all targets of the batch, so that a row is read from
@@ -600,11 +597,6 @@ __global__ void __launch_bounds__(kDpPThreads, 1)
     }
     ACRO_DP_T(t_comp)
     __syncthreads();  // s_v and the row buffer of this transition are free again
-    o0 = o1;
-    o1 = o2;
-    o2 = o3;
-    o3 = o4;
-    o4 = o5;
     ACRO_DP_T(t_tail)
   }
 #if ACRO_DP_TIMING
