@@ -516,3 +516,26 @@ def test_concurrent_callers(gpu):
     assert not errors, errors
     for got, exp in zip(results, expected):
         assert torch.equal(got, exp)
+
+
+def test_many_saved_poses_fall_back_to_small_ctas(gpu):
+    """The filter kernel is instantiated for 4, 9 and 14 warps per CTA and the launcher takes
+    the size with the most resident warps.  A robot whose self pairs keep many box poses
+    (8 links x 2 boxes, every pair of links two or more apart) needs ~25 KB of shared memory
+    per warp: only the small CTAs fit, and the verdicts still equal the plain FP64 kernel's."""
+    rng = np.random.default_rng(77)
+    links = []
+    for i in range(8):
+        dh = ab.DHLink(0.25, float([np.pi / 2, 0.0, -np.pi / 2, 0.3][i % 4]), 0.1, 0.0)
+        shapes = [ab.Box(0.2, 0.08, 0.08), ab.Box(0.08, 0.08, 0.15)]
+        tfs = [translation(-0.1, 0, 0), translation(0, 0, 0.05)]
+        links.append(ab.Link(dh, ab.JointType.revolute, ab.Scene(shapes, tfs)))
+    robot = ab.Robot(links)
+    cm = np.ones((8, 8), dtype=bool)
+    robot.collision_matrix = np.triu(cm, 2) | np.triu(cm, 2).T
+    robot.do_check_self_collision = True
+    q = rng.uniform(-np.pi, np.pi, (200_000, 8))
+    for scene in (scene16(), scene16(seed=9, n_boxes=40)):
+        hit = _all_variants_agree(robot, q, scene)
+        assert 0.05 < hit.mean() < 1.0
+    _all_variants_agree(robot, q, None, self_only=True)
