@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libacro_b200.so")
 
-SOURCES = ["abi.cu", "fk.cu", "fk_cc.cu", "fk_cc_wave.cu", "fk_cc_filt.cu", "jac_ik.cu", "path.cu", "planner.cu", "dp.cu"]
+SOURCES = ["abi.cu", "fk.cu", "fk_cc.cu", "fk_cc_wave.cu", "fk_cc_filt.cu", "jac_ik.cu", "path.cu", "swept.cu", "planner.cu", "dp.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

@@ -1091,6 +1091,20 @@ int acro_ik_wrist_f64(const double* R, const double* R_base_host, int64_t n, dou
   return finish(launch_ik_wrist(R, R_base_host, n, q_out, as_stream(stream)), "acro_ik_wrist_f64");
 }
 
+int acro_swept_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
+                      const double* q_goal, int64_t n_pairs, int32_t n_samples, uint32_t* mask,
+                      uint32_t* near_mask, double margin, void* stream) {
+  if (int rc = check_batch(robot, q_start, mask, n_pairs)) return rc;
+  if (int rc = check_scene_device(scene)) return rc;
+  if (n_pairs > 0 && !q_goal) return fail(ACRO_E_INVALID, "q_goal is NULL");
+  if (n_samples == 0) n_samples = 10;  // FCL: min(num_max_iterations = 10, ceil(1 / toc_err))
+  if (n_samples < 2) return fail(ACRO_E_INVALID, "n_samples must be 0 (FCL's 10) or >= 2");
+  if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
+  return finish(launch_swept_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_pairs,
+                                n_samples, mask, near_mask, margin, as_stream(stream)),
+                "acro_swept_cc_f64");
+}
+
 int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
                      const double* q_goal, int64_t n_segments, double max_q_step, uint32_t* mask,
                      void* stream) {

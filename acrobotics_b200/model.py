@@ -475,6 +475,50 @@ class Robot(RobotKinematics):
             return words if not host else words.cpu().numpy().view(np.uint32)
         return device.unpack_mask(words, e, host)
 
+    # ------------------------------------------------------------------
+    # swept (continuous) collision
+    # ------------------------------------------------------------------
+    def is_path_in_collision_batch(self, q_start, q_goal, scene, return_near=False,
+                                   margin=DEFAULT_MARGIN, n_samples=0, packed=False):
+        """(E, ndof) starts / goals -> bool (E,): the reference's ``is_path_in_collision``
+        (``robot.py:285-317``) per pair - every tool / link box as a moving object between its
+        two world poses under FCL's linear interpolated motion (``shapes.py:60-75``), base
+        boxes fixed, no self collision.  ``n_samples`` = 0 takes FCL's default request (10
+        samples of the motion, both end poses included).  The verdict is the stateless one:
+        python-fcl ORs ``is_collide`` into the result object the reference keeps per shape, so
+        the reference itself keeps answering True once a shape has collided."""
+        qs, host = self._q(q_start)
+        qg, _ = self._q(q_goal)
+        if qs.shape != qg.shape:
+            raise ValueError("q_start and q_goal must have the same shape")
+        e = qs.shape[0]
+        words = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda")
+        near = torch.zeros_like(words) if return_near else None
+        _native.check(
+            _native.load().acro_swept_cc_f64(
+                self._handle(),
+                scene.native_handle() if scene is not None else None,
+                qs.data_ptr(), qg.data_ptr(), e, int(n_samples), words.data_ptr(),
+                near.data_ptr() if near is not None else None, float(margin),
+                device.current_stream_ptr(),
+            ),
+            "acro_swept_cc_f64",
+        )
+        if packed:
+            res = words if not host else words.cpu().numpy().view(np.uint32)
+            if return_near:
+                return res, (near if not host else near.cpu().numpy().view(np.uint32))
+            return res
+        hit = device.unpack_mask(words, e, host)
+        if return_near:
+            return hit, device.unpack_mask(near, e, host)
+        return hit
+
+    def is_path_in_collision(self, q_start, q_goal, collection):
+        qs = np.asarray(q_start, dtype=np.float64).reshape(1, -1)
+        qg = np.asarray(q_goal, dtype=np.float64).reshape(1, -1)
+        return bool(self.is_path_in_collision_batch(qs, qg, collection)[0])
+
     def is_path_in_collision_discrete(self, q_start, q_goal, collection, max_q_step=0.1):
         qs = np.asarray(q_start, dtype=np.float64).reshape(1, -1)
         qg = np.asarray(q_goal, dtype=np.float64).reshape(1, -1)

@@ -252,6 +252,19 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
                      const double* q_goal, int64_t n_segments, double max_q_step, uint32_t* mask,
                      void* stream);
 
+/* ---- K7: swept (continuous) collision --------------------------------------------
+ * Robot.is_path_in_collision (robot.py:285-317) -> ShapeSoup.is_path_in_collision
+ * (geometry.py:68-81) -> fcl.continuousCollide(..., CCDM_LINEAR) (shapes.py:60-75) for E
+ * (q_start, q_goal) pairs: every tool / link box moves between its two world poses under
+ * FCL's InterpMotion (chord translation, constant-axis rotation), sampled n_samples times
+ * (0 = FCL's default request: 10) with the Box-Box test at every sample; base boxes fixed;
+ * no self collision.  mask bit e = the pair collides.  near_mask (or NULL) / margin as in
+ * acro_fk_cc_f64.  Stateless: the reference's python-fcl result object is sticky per
+ * Shape.                                                          */
+int acro_swept_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
+                      const double* q_goal, int64_t n_pairs, int32_t n_samples, uint32_t* mask,
+                      uint32_t* near_mask, double margin, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------
  * DFMA / FFMA chain micro-benchmark: the compute-roofline denominator.  Returns
  * achieved TFLOP/s (FMA = 2 flop) in *tflops; runs on the current device.        */

@@ -294,6 +294,131 @@ def is_path_in_collision_discrete(spec, scene, q_start, q_goal, max_q_step=0.1):
 
 
 # ----------------------------------------------------------------------------
+# swept collision (fcl.continuousCollide as the reference calls it; oracle/fcl_ccd.py)
+# ----------------------------------------------------------------------------
+CCD_SAMPLES = 10  # FCL: min(num_max_iterations = 10, ceil(1 / toc_err))
+
+
+def _mat_to_quat(m):
+    """Eigen ``Quaternion(Matrix3)`` for a stack (...,3,3) -> (...,4) as (w, x, y, z)."""
+    m = np.asarray(m, dtype=np.float64)
+    t = m[..., 0, 0] + m[..., 1, 1] + m[..., 2, 2]
+    out = np.empty(m.shape[:-2] + (4,))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        s = np.sqrt(np.maximum(t + 1.0, 0.0))
+        w0 = 0.5 * s
+        r = 0.5 / s
+        cand = [
+            np.stack(
+                [w0, (m[..., 2, 1] - m[..., 1, 2]) * r, (m[..., 0, 2] - m[..., 2, 0]) * r,
+                 (m[..., 1, 0] - m[..., 0, 1]) * r], axis=-1)
+        ]
+        for i in range(3):
+            j, k = (i + 1) % 3, (i + 2) % 3
+            s = np.sqrt(np.maximum(m[..., i, i] - m[..., j, j] - m[..., k, k] + 1.0, 0.0))
+            r = 0.5 / s
+            c = np.empty(m.shape[:-2] + (4,))
+            c[..., 1 + i] = 0.5 * s
+            c[..., 0] = (m[..., k, j] - m[..., j, k]) * r
+            c[..., 1 + j] = (m[..., j, i] + m[..., i, j]) * r
+            c[..., 1 + k] = (m[..., k, i] + m[..., i, k]) * r
+            cand.append(c)
+    i_max = np.zeros(t.shape, dtype=int)
+    i_max = np.where(m[..., 1, 1] > m[..., 0, 0], 1, i_max)
+    dia = np.take_along_axis(
+        np.stack([m[..., 0, 0], m[..., 1, 1], m[..., 2, 2]], axis=-1), i_max[..., None], axis=-1
+    )[..., 0]
+    i_max = np.where(m[..., 2, 2] > dia, 2, i_max)
+    sel = np.where(t > 0.0, 0, 1 + i_max)
+    for b in range(4):
+        out = np.where((sel == b)[..., None], cand[b], out)
+    return out
+
+
+def _quat_to_mat(q):
+    w, x, y, z = (q[..., i] for i in range(4))
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    R = np.empty(q.shape[:-1] + (3, 3))
+    R[..., 0, 0] = 1 - (tyy + tzz)
+    R[..., 0, 1] = txy - twz
+    R[..., 0, 2] = txz + twy
+    R[..., 1, 0] = txy + twz
+    R[..., 1, 1] = 1 - (txx + tzz)
+    R[..., 1, 2] = tyz - twx
+    R[..., 2, 0] = txz - twy
+    R[..., 2, 1] = tyz + twx
+    R[..., 2, 2] = 1 - (txx + tyy)
+    return R
+
+
+def _quat_mul(a, b):
+    aw, ax, ay, az = (a[..., i] for i in range(4))
+    bw, bx, by, bz = (b[..., i] for i in range(4))
+    return np.stack(
+        [aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+         aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx], axis=-1)
+
+
+def interp_motion(R1, t1, R2, t2, n_samples=CCD_SAMPLES):
+    """FCL ``InterpMotion`` sampled at ``t = i / (n - 1)``: stacks (..., n, 3, 3), (..., n, 3)."""
+    q = _mat_to_quat(R2 @ np.swapaxes(R1, -1, -2))
+    n = np.linalg.norm(q[..., 1:], axis=-1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        angle = np.where(n != 0.0, 2.0 * np.arctan2(n, np.abs(q[..., 0])), 0.0)
+        axis = q[..., 1:] / np.where(q[..., 0] < 0.0, -n, n)[..., None]
+    axis = np.where((n != 0.0)[..., None], axis, np.array([1.0, 0.0, 0.0]))
+    q1 = _mat_to_quat(R1)
+    ts = np.arange(n_samples) / (n_samples - 1)
+    half = 0.5 * angle[..., None] * ts
+    dq = np.concatenate([np.cos(half)[..., None], np.sin(half)[..., None] * axis[..., None, :]], axis=-1)
+    R = _quat_to_mat(_quat_mul(dq, q1[..., None, :]))
+    p = t1[..., None, :] + ts[:, None] * (t2 - t1)[..., None, :]
+    return R, p
+
+
+def swept_margins(spec: RobotSpec, scene, q_start, q_goal, chunk=5000, n_samples=CCD_SAMPLES):
+    """Per (q_start, q_goal) pair the smallest SAT decision quantity over everything the
+    stateless ``Robot.is_path_in_collision`` (robot.py:285-317) tests: tool and link boxes
+    as moving objects between their start and target world poses (geometry.py:68-81 ->
+    shapes.py:60-75 -> FCL naive solver over ``InterpMotion``), base boxes fixed at
+    ``tf_base``.  No self collision (robot.py:288).  ``g <= 0`` <=> the reference returns True
+    on fresh ``Shape`` objects."""
+    q_start = np.atleast_2d(np.asarray(q_start, dtype=np.float64))
+    q_goal = np.atleast_2d(np.asarray(q_goal, dtype=np.float64))
+    N = q_start.shape[0]
+    sh, sR, sT = scene if isinstance(scene, tuple) else scene_arrays(scene)
+    gmin = np.full(N, np.inf)
+    if len(sh) == 0 or not spec.boxes:
+        return gmin
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        Ra, ca = world_boxes(spec, q_start[lo:hi])
+        Rb, cb = world_boxes(spec, q_goal[lo:hi])
+        g = np.full(hi - lo, np.inf)
+        for b, box in enumerate(spec.boxes):
+            if box.group == GROUP_BASE:
+                R, p = Ra[:, b, None], ca[:, b, None]  # robot.py:303-306: fixed
+            else:
+                R, p = interp_motion(Ra[:, b], ca[:, b], Rb[:, b], cb[:, b], n_samples)
+            _, gp = sat(box.half, R[:, :, None], p[:, :, None], sh[None, None], sR[None, None],
+                        sT[None, None])
+            g = np.minimum(g, gp.reshape(hi - lo, -1).min(axis=1))
+        gmin[lo:hi] = g
+    return gmin
+
+
+def is_path_in_collision(spec: RobotSpec, scene, q_start, q_goal, margin=None):
+    g = swept_margins(spec, scene, q_start, q_goal)
+    hit = ~(g > 0)
+    if margin is None:
+        return hit
+    return hit, np.abs(g) <= margin
+
+
+# ----------------------------------------------------------------------------
 # analytical inverse kinematics
 # ----------------------------------------------------------------------------
 def tf_inverse(T):

@@ -8,6 +8,8 @@ What runs unchanged: the reference's own ``link.py``, ``robot.py``,
 ``inverse_kinematics/*``.  What is restated because the dependency is missing:
 
 * ``fcl.collide`` for Box-Box -> ``oracle.fcl_boxbox`` (FCL ``boxBox2``);
+* ``fcl.continuousCollide`` (CCDM_LINEAR, naive solver, python-fcl's sticky result) ->
+  ``oracle.fcl_ccd``;
 * ``acrolib.geometry.translation / pose_x / pose_z / rot_x / rot_y / rot_z``
   (textbook homogeneous transforms; semantics confirmed by reference
   ``tests/test_robot_kinematics.py:100-107`` and the README golden vectors);
@@ -101,6 +103,8 @@ def _fcl_collide(o1, o2, request=None, result=None):
 
 
 def _install_stubs():
+    from . import fcl_ccd
+
     def mod(name, **attrs):
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
@@ -114,13 +118,13 @@ def _install_stubs():
         Transform=_FclTransform,
         CollisionObject=_FclCollisionObject,
         collide=_fcl_collide,
-        continuousCollide=MagicMock(),
+        continuousCollide=fcl_ccd.continuous_collide,
         CollisionGeometry=MagicMock(),
         CollisionRequest=MagicMock,
         CollisionResult=MagicMock,
-        ContinuousCollisionRequest=MagicMock,
-        ContinuousCollisionResult=MagicMock,
-        CCDMotionType=MagicMock(),
+        ContinuousCollisionRequest=fcl_ccd.ContinuousCollisionRequest,
+        ContinuousCollisionResult=fcl_ccd.ContinuousCollisionResult,
+        CCDMotionType=fcl_ccd.CCDMotionType,
     )
     sys.modules["casadi"] = MagicMock(name="casadi")
     mpl = mod("matplotlib")
