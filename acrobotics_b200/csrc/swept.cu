@@ -97,8 +97,12 @@ __device__ __forceinline__ void rotate_about(const double* ax, double theta, con
       R[3 * r + col] = fma(D[3 * r + 2], Ra[6 + col], fma(D[3 * r + 1], Ra[3 + col], D[3 * r] * Ra[col]));
 }
 
+#ifndef ACRO_SWEPT_MIN_CTAS
+#define ACRO_SWEPT_MIN_CTAS 2
+#endif
+
 template <int NDOF, bool MARGIN>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
     swept_cc_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
                     const double* __restrict__ q0, const double* __restrict__ q1, int64_t n,
                     int n_samples, bool vec, uint32_t* __restrict__ mask,
@@ -110,9 +114,22 @@ __global__ void __launch_bounds__(kTile)
 
   const int64_t idx = (int64_t)blockIdx.x * kTile + threadIdx.x;
   const bool active = idx < n;
-  double qa[NDOF], qb[NDOF];
-  load_q_direct<double, NDOF>(qa, q0, idx, n, ACRO_Q_AOS, vec);
-  load_q_direct<double, NDOF>(qb, q1, idx, n, ACRO_Q_AOS, vec);
+  // joint values: read as rows into registers, then parked in shared memory (column tid) so
+  // that the ROLLED joint loop below can index them - one copy of the sweep code instead of
+  // NDOF + 1 (the unrolled kernel stalled on instruction fetch: ncu no_instruction 4.7 of 8.4
+  // cycles per issue)
+  double* s_qa = s_scene + sc.n * kSceneStride;
+  double* s_qb = s_qa + NDOF * kTile;
+  {
+    double qa[NDOF], qb[NDOF];
+    load_q_direct<double, NDOF>(qa, q0, idx, n, ACRO_Q_AOS, vec);
+    load_q_direct<double, NDOF>(qb, q1, idx, n, ACRO_Q_AOS, vec);
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) {
+      s_qa[i * kTile + threadIdx.x] = qa[i];
+      s_qb[i * kTile + threadIdx.x] = qb[i];
+    }
+  }
 
   Verdict<double, MARGIN> v;
   const double pad = MARGIN ? margin : 0.0;
@@ -186,15 +203,17 @@ __global__ void __launch_bounds__(kTile)
     }
   };
 
-  // fully unrolled like every other chain loop of the library: qa / qb stay in registers
-#pragma unroll
-  for (int i = 0; i < NDOF; ++i) {
+  // slots 1..NDOF: DH step of both chains, then that link's boxes; slot NDOF + 1: the tool on
+  // the last link frame (robot.py:296-300)
+#pragma unroll 1
+  for (int slot = 1; slot <= NDOF + 1; ++slot) {
     if (__all_sync(full, !active || v.done(margin))) break;
-    chain_step<double>(Ta, rb, i, qa[i]);
-    chain_step<double>(Tb, rb, i, qb[i]);
-    sweep_slot(i + 1);
+    if (slot <= NDOF) {
+      chain_step<double>(Ta, rb, slot - 1, s_qa[(slot - 1) * kTile + threadIdx.x]);
+      chain_step<double>(Tb, rb, slot - 1, s_qb[(slot - 1) * kTile + threadIdx.x]);
+    }
+    sweep_slot(slot);
   }
-  if (!__all_sync(full, !active || v.done(margin))) sweep_slot(NDOF + 1);  // the tool (robot.py:296-300)
 
   const unsigned word = __ballot_sync(full, active && v.hit);
   unsigned near_word = 0;
@@ -211,8 +230,8 @@ cudaError_t launch_swept_cc(const RobotDev<double>& rb, SceneView<double> sc, co
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL || n_samples < 2) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(double) * sc.n * kSceneStride;
   ACRO_DISPATCH_NDOF(rb.ndof, {
+    const size_t smem = sizeof(double) * (sc.n * kSceneStride + 2 * NDOF * kTile);
     const bool vec = NDOF % 2 == 0 && aligned16(q0) && aligned16(q1);
     if (near_mask)
       swept_cc_kernel<NDOF, true><<<(unsigned)tiles, kTile, smem, st>>>(
