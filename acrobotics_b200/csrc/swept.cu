@@ -6,7 +6,7 @@
 // (src/acrobotics/shapes.py:60-75) for a batch of (q_start, q_goal) pairs.
 //
 // What that FCL call computes (default request: naive solver, num_max_iterations = 10,
-// toc_err = 1e-4; see oracle/fcl_ccd.py): every tool / link box is its own moving object
+// toc_err = 1e-4): every tool / link box is its own moving object
 // between its world pose at q_start and at q_goal under FCL's InterpMotion - the centre on the
 // CHORD between the two positions, the orientation about one fixed axis (angle-axis of
 // R_goal R_start^T, angle in [0, pi]) at constant rate - sampled at t = i / (n - 1),

@@ -479,21 +479,28 @@ class Robot(RobotKinematics):
     # swept (continuous) collision
     # ------------------------------------------------------------------
     def is_path_in_collision_batch(self, q_start, q_goal, scene, return_near=False,
-                                   margin=DEFAULT_MARGIN, n_samples=0, packed=False):
+                                   margin=DEFAULT_MARGIN, n_samples=0, packed=False, out=None):
         """(E, ndof) starts / goals -> bool (E,): the reference's ``is_path_in_collision``
         (``robot.py:285-317``) per pair - every tool / link box as a moving object between its
         two world poses under FCL's linear interpolated motion (``shapes.py:60-75``), base
         boxes fixed, no self collision.  ``n_samples`` = 0 takes FCL's default request (10
         samples of the motion, both end poses included).  The verdict is the stateless one:
         python-fcl ORs ``is_collide`` into the result object the reference keeps per shape, so
-        the reference itself keeps answering True once a shape has collided."""
+        the reference itself keeps answering True once a shape has collided.
+        ``packed`` / ``out``: as in ``is_in_collision_batch``."""
         qs, host = self._q(q_start)
         qg, _ = self._q(q_goal)
         if qs.shape != qg.shape:
             raise ValueError("q_start and q_goal must have the same shape")
         e = qs.shape[0]
-        words = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda")
-        near = torch.zeros_like(words) if return_near else None
+        if out is not None:
+            if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.int32
+                    and out.is_contiguous() and out.numel() >= device.mask_words(e)):
+                raise ValueError("out must be a contiguous CUDA int32 tensor of >= ceil(E/32) words")
+            words, packed, host = out, True, False
+        else:
+            words = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda")
+        near = torch.zeros(device.mask_words(e), dtype=torch.int32, device="cuda") if return_near else None
         _native.check(
             _native.load().acro_swept_cc_f64(
                 self._handle(),

@@ -222,6 +222,24 @@ def is_path_in_collision_discrete_sharded(robot, q_start, q_goal, scene, max_q_s
     return sh.mask() if packed else device.unpack_mask(sh.mask(), e, host=False)
 
 
+def is_path_in_collision_sharded(robot, q_start, q_goal, scene, n_samples=0, group=None,
+                                 packed: bool = False):
+    """Swept collision ``Robot.is_path_in_collision`` (robot.py:285-317) for (E, ndof) pair
+    arrays every rank holds: pairs are sharded like configurations (rank r sweeps its
+    contiguous, word-aligned block straight into its slice of the gather buffer), the verdict
+    words all-gathered.  No other exchange: the pairs are independent."""
+    from . import device
+
+    e = int(q_start.shape[0])
+
+    def into(lo, hi, out):
+        robot.is_path_in_collision_batch(q_start[lo:hi], q_goal[lo:hi], scene, n_samples=n_samples,
+                                         out=out)
+
+    sh = check_sharded(e, into, group, 1, q_start.device)
+    return sh.mask() if packed else device.unpack_mask(sh.mask(), e, host=False)
+
+
 def joint_solutions_csr_sharded(robot, T, scene, group=None, gather_solutions: bool = False,
                                 solve_local: Callable = None, trim: bool = True):
     """Planner sweep (``path_to_joint_solutions``, reference planning/sampling_based.py:94-106)

@@ -420,6 +420,33 @@ def run_ours(args):
               "collective": "all-gather of per-point counts (int64) and per-pose free-branch masks (uint8)"}
         del T, res
 
+    # ---- K7 swept collision (Robot.is_path_in_collision, robot.py:285-317): pairs whose start
+    # pose is collision-free (the planner's case), sharded over the ranks like configurations
+    swept = None
+    if not args.no_swept:
+        E = args.swept_pairs
+        pool = random_configs_device(6 * E, 6, seed=777)  # same pairs on every rank
+        keep = ~robot.is_in_collision_batch(pool, scene)
+        qs_sw = pool[keep][:E].contiguous()
+        E = int(qs_sw.shape[0])
+        gen = torch.Generator(device="cuda").manual_seed(778)
+        qg_sw = qs_sw + (torch.rand(qs_sw.shape, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1) * 0.3
+        del pool, keep
+        res = {}
+
+        def swept_step():
+            res["w"] = sharding.is_path_in_collision_sharded(robot, qs_sw, qg_sw, scene, packed=True)
+
+        wms = _time_steps(torch, dist, world, swept_step, max(2, args.steps // 2), 3)
+        hits = int(sum(bin(int(x) & 0xffffffff).count("1") for x in res["w"][: (E + 31) // 32].cpu().tolist()))
+        swept = {"pairs": E, "samples_per_pair": 10, "dq_span": 0.3, "start_poses": "collision-free",
+                 "ms_per_step": wms, "pairs_per_s": E / (wms * 1e-3),
+                 "pose_checks_per_s": 10 * E / (wms * 1e-3), "hit_rate": hits / max(E, 1),
+                 "n_gpus": world, "partition": "contiguous word-aligned pair blocks per rank",
+                 "collective": "in-place all-gather of the verdict words",
+                 "path": "sharding.is_path_in_collision_sharded -> acro_swept_cc_f64 (FP64)"}
+        del qs_sw, qg_sw, res
+
     # ---- C2 / C4 (single-GPU configs; reported at N = 1)
     c2 = c4 = None
     if world == 1 and not args.no_c24:
@@ -579,7 +606,7 @@ def run_ours(args):
                         "bytes_per_config": BYTES_PER_CONFIG},
                 "profile_source": prof.get("source"),
             },
-            "strong": strong, "c2": c2, "c4": c4, "c5": c5, "parity": parity,
+            "strong": strong, "c2": c2, "c4": c4, "c5": c5, "swept": swept, "parity": parity,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -617,6 +644,8 @@ def main():
     ap.add_argument("--c5-points", type=int, default=10_000)
     ap.add_argument("--c5-samples", type=int, default=400)
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-swept", action="store_true")
+    ap.add_argument("--swept-pairs", type=int, default=2_000_000)
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-c24", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

@@ -58,6 +58,9 @@ def test_path_segments_and_planner_sweep_sharded(gpu):
     want = k.is_path_in_collision_discrete_batch(qs, qg, scene, 0.1)
     got = sharding.is_path_in_collision_discrete_sharded(k, qs, qg, scene, 0.1)
     assert torch.equal(got, want)
+    want = k.is_path_in_collision_batch(qs, qg, scene)
+    assert torch.equal(sharding.is_path_in_collision_sharded(k, qs, qg, scene), want)
+    assert 0.05 < float(want.float().mean()) < 0.95
     P, S = 40, 25
     T = k.fk_batch(random_configs_device(P * S, 6, seed=6)).view(P, S, 4, 4)
     q_free, off, _, _, free = joint_solutions_csr(k, T, scene, return_all=True)

@@ -186,3 +186,60 @@ def test_planner_sweep_sharded_over_path_points(tmp_path, world, P, S):
         assert np.array_equal(g["q_local"], rows.numpy()[off[lo]:off[hi]])
         covered += hi - lo
     assert covered == P
+
+
+# ---------------------------------------------------------------------------
+# swept collision (K7) sharded over pairs: a stub robot whose batch call is the numpy oracle
+# ---------------------------------------------------------------------------
+class _OracleSweepRobot:
+    def __init__(self):
+        import acrobotics_b200 as ab
+        from oracle import np_oracle as no
+
+        self.no, self.spec = no, no.spec_from_robot(ab.Kuka())
+
+    def is_path_in_collision_batch(self, q_start, q_goal, scene, n_samples=0, out=None):
+        g = self.no.swept_margins(self.spec, scene, q_start.numpy(), q_goal.numpy(),
+                                  n_samples=n_samples or self.no.CCD_SAMPLES)
+        hit = ~(g > 0)
+        bits = np.concatenate([hit, np.zeros((-len(hit)) % 32, bool)])
+        words = torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy())
+        out[: len(words)] = words
+
+
+def _swept_inputs(n):
+    from acrobotics_b200.synthetic import random_configs
+
+    qs = random_configs(n, 6, seed=11)
+    return qs, qs + np.random.default_rng(12).uniform(-0.7, 0.7, qs.shape)
+
+
+def _swept_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from acrobotics_b200.synthetic import scene16
+        from oracle import np_oracle as no
+
+        qs, qg = _swept_inputs(n)
+        words = sharding.is_path_in_collision_sharded(
+            _OracleSweepRobot(), torch.from_numpy(qs), torch.from_numpy(qg),
+            no.scene_arrays(scene16()), packed=True)
+        np.save(os.path.join(out_dir, f"swept{rank}.npy"), words.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 300), (3, 65)])
+def test_swept_pairs_sharded_equal_single_rank(tmp_path, world, n):
+    import acrobotics_b200 as ab
+    from acrobotics_b200.synthetic import scene16
+    from oracle import np_oracle as no
+
+    mp.spawn(_swept_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    qs, qg = _swept_inputs(n)
+    g = no.swept_margins(no.spec_from_robot(ab.Kuka()), no.scene_arrays(scene16()), qs, qg)
+    for r in range(world):
+        w = np.load(tmp_path / f"swept{r}.npy").view(np.uint32)
+        bits = np.unpackbits(w.view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (bits == ~(g > 0)).all()
