@@ -600,6 +600,11 @@ int acro_device_count(void) {
   return n;
 }
 
+// K7: batches of at least this many pairs go to the persistent kernel
+static constexpr int64_t kSweptPersistentMin = 4096;
+static std::atomic<int> g_swept_persistent{0};
+static bool swept_persistent() { return g_swept_persistent.load() != 0; }
+
 int acro_set_option(const char* name, const char* value) {
   if (!name || !value) return fail(ACRO_E_INVALID, "NULL option");
   const std::string n(name), v(value);
@@ -619,6 +624,10 @@ int acro_set_option(const char* name, const char* value) {
     const int d = std::atoi(value);
     if (d < 8 || d > 160) return fail(ACRO_E_INVALID, "k2_grid: 8..160 cells per axis");
     g_grid_dim.store(d);
+    return 0;
+  }
+  if (n == "swept_persistent") {
+    g_swept_persistent.store(std::atoi(value) != 0 ? 1 : 0);
     return 0;
   }
   return fail(ACRO_E_INVALID, "unknown option");
@@ -1100,9 +1109,24 @@ int acro_swept_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doub
   if (n_samples == 0) n_samples = 10;  // FCL: min(num_max_iterations = 10, ceil(1 / toc_err))
   if (n_samples < 2) return fail(ACRO_E_INVALID, "n_samples must be 0 (FCL's 10) or >= 2");
   if (near_mask && !(margin >= 0.0)) return fail(ACRO_E_INVALID, "margin must be >= 0");
-  return finish(launch_swept_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_pairs,
-                                n_samples, mask, near_mask, margin, as_stream(stream)),
-                "acro_swept_cc_f64");
+  cudaStream_t st = as_stream(stream);
+  // "swept_persistent" = "1": large batches go to the persistent kernel (lanes take pairs from
+  // a counter; the counter word comes from the stream-ordered pool).  Off by default: measured
+  // slower than one thread per pair (profiles/r2_swept_ab.jsonl).
+  unsigned long long* counter = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (n_pairs >= kSweptPersistentMin && swept_persistent()) {
+    e = cudaMallocAsync(reinterpret_cast<void**>(&counter), sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+  }
+  if (e == cudaSuccess)
+    e = launch_swept_cc(robot->d64, view_of<double>(scene), q_start, q_goal, n_pairs, n_samples,
+                        mask, near_mask, margin, counter, st);
+  if (counter) {
+    cudaError_t e2 = cudaFreeAsync(counter, st);
+    if (e == cudaSuccess) e = e2;
+  }
+  return finish(e, "acro_swept_cc_f64");
 }
 
 int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,

@@ -76,7 +76,8 @@ cudaError_t launch_path_cc(const RobotDev<double>& rb, SceneView<double> sc, con
 // K7 (swept.cu): FCL's continuous collision (InterpMotion, naive solver) of (q0, q1) pairs
 cudaError_t launch_swept_cc(const RobotDev<double>& rb, SceneView<double> sc, const double* q0,
                             const double* q1, int64_t n, int n_samples, uint32_t* mask,
-                            uint32_t* near_mask, double margin, cudaStream_t st);
+                            uint32_t* near_mask, double margin, unsigned long long* counter,
+                            cudaStream_t st);
 
 // filtered sweep (FP32 filter + exact FP64 pass over the ambiguous segments); `scratch` holds
 // 8 * ceil(ceil(n_seg / 32) / 2) + 8 bytes

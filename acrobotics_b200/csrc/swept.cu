@@ -97,6 +97,108 @@ __device__ __forceinline__ void rotate_about(const double* ax, double theta, con
       R[3 * r + col] = fma(D[3 * r + 2], Ra[6 + col], fma(D[3 * r + 1], Ra[3 + col], D[3 * r] * Ra[col]));
 }
 
+// One moving box, set up: its world poses on the two chains (Wa kept, the chord l = pb - pa)
+// and the chord cull - a scene box whose own face axis separates it from the sphere of radius
+// |half| swept along the chord is separated at every sample in FCL's face-axis test.
+// Returns the bit set of the scene boxes that remain.
+__device__ __forceinline__ uint64_t setup_moving_box(const BoxDev<double>& bx, const Tf<double>& Ta,
+                                                     const Tf<double>& Tb, const double* s_scene,
+                                                     int n_scene, double pad, Tf<double>& Wa,
+                                                     double* l, double& angle, double* ax) {
+  Tf<double> Wb;
+  tf_mul<double>(Wa, Ta, bx.off);
+  tf_mul<double>(Wb, Tb, bx.off);
+  l[0] = Wb.p[0] - Wa.p[0];
+  l[1] = Wb.p[1] - Wa.p[1];
+  l[2] = Wb.p[2] - Wa.p[2];
+  const double reach = bx.radius + pad +
+                       0.5 * sqrt(fma(l[2], l[2], fma(l[1], l[1], l[0] * l[0]))) * (1.0 + 1e-12) +
+                       1e-12;
+  const double mid[3] = {fma(0.5, l[0], Wa.p[0]), fma(0.5, l[1], Wa.p[1]), fma(0.5, l[2], Wa.p[2])};
+  uint64_t cand = 0;
+  for (int j = 0; j < n_scene; ++j) {
+    const double* b2 = s_scene + j * kSceneStride;
+    const double d0 = mid[0] - b2[kOB_T + 0], d1 = mid[1] - b2[kOB_T + 1],
+                 d2 = mid[2] - b2[kOB_T + 2];
+    const double y0 = fma(b2[6], d2, fma(b2[3], d1, b2[0] * d0));
+    const double y1 = fma(b2[7], d2, fma(b2[4], d1, b2[1] * d0));
+    const double y2 = fma(b2[8], d2, fma(b2[5], d1, b2[2] * d0));
+    const bool sep = (fabs(y0) > b2[kOB_H + 0] + reach) | (fabs(y1) > b2[kOB_H + 1] + reach) |
+                     (fabs(y2) > b2[kOB_H + 2] + reach);
+    if (!sep) cand |= (1ull << j);
+  }
+  if (cand != 0) relative_angle_axis(Wa.r, Wb.r, angle, ax);
+  return cand;
+}
+
+// One sample of FCL's loop for one moving box: pose at t = s / (n - 1), Box-Box vs the candidates
+template <bool MARGIN>
+__device__ __forceinline__ void sample_moving_box(const BoxDev<double>& bx, const Tf<double>& Wa,
+                                                  const double* l, double angle, const double* ax,
+                                                  int s, int n_samples, uint64_t cand,
+                                                  const double* s_scene, double margin,
+                                                  Verdict<double, MARGIN>& v) {
+  const double pad = MARGIN ? margin : 0.0;
+  const double t = (double)s / (double)(n_samples - 1);
+  double R[9], c[3];
+  rotate_about(ax, t * angle, Wa.r, R);
+  c[0] = fma(t, l[0], Wa.p[0]);
+  c[1] = fma(t, l[1], Wa.p[1]);
+  c[2] = fma(t, l[2], Wa.p[2]);
+  uint64_t todo = cand;
+  while (todo != 0 && !v.done(margin)) {
+    const int j = __ffsll((long long)todo) - 1;
+    todo &= todo - 1;
+    const double* b2 = s_scene + j * kSceneStride;
+    if (cull_separated<double>(bx.half[0], bx.half[1], bx.half[2], bx.radius, R, c, b2, pad))
+      continue;
+    double g;
+    if (!sat_separated<double>(bx.half[0], bx.half[1], bx.half[2], R, c, b2, pad, g)) {
+      if (MARGIN) {
+        v.gmin = min(v.gmin, g);
+        if (g <= 0.0) v.hit = true;
+      } else {
+        v.hit = true;
+      }
+    }
+  }
+}
+
+// The boxes of one slot (a link's, or the tool's) as moving objects between their poses on the
+// two chains.
+template <bool MARGIN>
+__device__ __forceinline__ void sweep_slot_boxes(const RobotDev<double>& rb, int slot,
+                                                 const Tf<double>& Ta, const Tf<double>& Tb,
+                                                 const double* s_scene, int n_scene,
+                                                 int n_samples, double margin,
+                                                 Verdict<double, MARGIN>& v) {
+  const double pad = MARGIN ? margin : 0.0;
+  for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
+    const BoxDev<double>& bx = rb.boxes[b];
+    if (v.done(margin) || n_scene == 0) continue;
+    Tf<double> Wa;
+    double l[3], angle, ax[3];
+    const uint64_t cand = setup_moving_box(bx, Ta, Tb, s_scene, n_scene, pad, Wa, l, angle, ax);
+    if (cand == 0) continue;
+    for (int s = 0; s < n_samples && !v.done(margin); ++s)
+      sample_moving_box<MARGIN>(bx, Wa, l, angle, ax, s, n_samples, cand, s_scene, margin, v);
+  }
+}
+
+// geometry_base: fixed at tf_base, one discrete test (robot.py:303-306)
+template <bool MARGIN>
+__device__ __forceinline__ void base_slot_boxes(const RobotDev<double>& rb, const Tf<double>& T0,
+                                                const double* s_scene, int n_scene,
+                                                double margin, Verdict<double, MARGIN>& v) {
+  for (int b = rb.slot_begin[0]; b < rb.slot_begin[1]; ++b) {
+    const BoxDev<double>& bx = rb.boxes[b];
+    Tf<double> W;
+    tf_mul<double>(W, T0, bx.off);
+    if (!v.done(margin) && n_scene > 0)
+      box_vs_scene<double, MARGIN>(bx, W.r, W.p, s_scene, n_scene, margin, v);
+  }
+}
+
 #ifndef ACRO_SWEPT_MIN_CTAS
 #define ACRO_SWEPT_MIN_CTAS 2
 #endif
@@ -132,76 +234,13 @@ __global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
   }
 
   Verdict<double, MARGIN> v;
-  const double pad = MARGIN ? margin : 0.0;
   const unsigned full = 0xffffffffu;
   const int n_scene = sc.n;
   Tf<double> Ta, Tb;
   tf_load<double>(Ta, rb.base);
   Tb = Ta;
 
-  // geometry_base: fixed at tf_base, one discrete test (robot.py:303-306)
-  for (int b = rb.slot_begin[0]; b < rb.slot_begin[1]; ++b) {
-    const BoxDev<double>& bx = rb.boxes[b];
-    Tf<double> W;
-    tf_mul<double>(W, Ta, bx.off);
-    if (active && !v.done(margin) && n_scene > 0)
-      box_vs_scene<double, MARGIN>(bx, W.r, W.p, s_scene, n_scene, margin, v);
-  }
-
-  auto sweep_slot = [&](int slot) {
-    for (int b = rb.slot_begin[slot]; b < rb.slot_begin[slot + 1]; ++b) {
-      const BoxDev<double>& bx = rb.boxes[b];
-      if (!active || v.done(margin) || n_scene == 0) continue;
-      Tf<double> Wa, Wb;
-      tf_mul<double>(Wa, Ta, bx.off);
-      tf_mul<double>(Wb, Tb, bx.off);
-      // chord cull: sphere of radius |half| swept along the chord vs the scene box's own faces
-      const double l0 = Wb.p[0] - Wa.p[0], l1 = Wb.p[1] - Wa.p[1], l2 = Wb.p[2] - Wa.p[2];
-      const double reach =
-          bx.radius + pad + 0.5 * sqrt(fma(l2, l2, fma(l1, l1, l0 * l0))) * (1.0 + 1e-12) + 1e-12;
-      const double mid[3] = {fma(0.5, l0, Wa.p[0]), fma(0.5, l1, Wa.p[1]), fma(0.5, l2, Wa.p[2])};
-      uint64_t cand = 0;
-      for (int j = 0; j < n_scene; ++j) {
-        const double* b2 = s_scene + j * kSceneStride;
-        const double d0 = mid[0] - b2[kOB_T + 0], d1 = mid[1] - b2[kOB_T + 1],
-                     d2 = mid[2] - b2[kOB_T + 2];
-        const double y0 = fma(b2[6], d2, fma(b2[3], d1, b2[0] * d0));
-        const double y1 = fma(b2[7], d2, fma(b2[4], d1, b2[1] * d0));
-        const double y2 = fma(b2[8], d2, fma(b2[5], d1, b2[2] * d0));
-        const bool sep = (fabs(y0) > b2[kOB_H + 0] + reach) | (fabs(y1) > b2[kOB_H + 1] + reach) |
-                         (fabs(y2) > b2[kOB_H + 2] + reach);
-        if (!sep) cand |= (1ull << j);
-      }
-      if (cand == 0) continue;
-      double angle, ax[3];
-      relative_angle_axis(Wa.r, Wb.r, angle, ax);
-      for (int s = 0; s < n_samples && !v.done(margin); ++s) {
-        const double t = (double)s / (double)(n_samples - 1);
-        double R[9], c[3];
-        rotate_about(ax, t * angle, Wa.r, R);
-        c[0] = fma(t, l0, Wa.p[0]);
-        c[1] = fma(t, l1, Wa.p[1]);
-        c[2] = fma(t, l2, Wa.p[2]);
-        uint64_t todo = cand;
-        while (todo != 0 && !v.done(margin)) {
-          const int j = __ffsll((long long)todo) - 1;
-          todo &= todo - 1;
-          const double* b2 = s_scene + j * kSceneStride;
-          if (cull_separated<double>(bx.half[0], bx.half[1], bx.half[2], bx.radius, R, c, b2, pad))
-            continue;
-          double g;
-          if (!sat_separated<double>(bx.half[0], bx.half[1], bx.half[2], R, c, b2, pad, g)) {
-            if (MARGIN) {
-              v.gmin = min(v.gmin, g);
-              if (g <= 0.0) v.hit = true;
-            } else {
-              v.hit = true;
-            }
-          }
-        }
-      }
-    }
-  };
+  if (active) base_slot_boxes<MARGIN>(rb, Ta, s_scene, n_scene, margin, v);
 
   // slots 1..NDOF: DH step of both chains, then that link's boxes; slot NDOF + 1: the tool on
   // the last link frame (robot.py:296-300)
@@ -212,7 +251,7 @@ __global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
       chain_step<double>(Ta, rb, slot - 1, s_qa[(slot - 1) * kTile + threadIdx.x]);
       chain_step<double>(Tb, rb, slot - 1, s_qb[(slot - 1) * kTile + threadIdx.x]);
     }
-    sweep_slot(slot);
+    if (active) sweep_slot_boxes<MARGIN>(rb, slot, Ta, Tb, s_scene, n_scene, n_samples, margin, v);
   }
 
   const unsigned word = __ballot_sync(full, active && v.hit);
@@ -224,21 +263,148 @@ __global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
   }
 }
 
+// Persistent variant for large batches: every LANE owns one pair at a time and advances it by
+// one step per round - either the set-up of its next box (DH steps when a slot closes, world
+// poses, chord cull, angle-axis) or ONE sample of the box in progress; a lane whose pair is
+// decided (first colliding sample, or all slots clear) sets its verdict bit and takes the next
+// pair from a grid-wide counter, so pairs that end at their start pose, boxes without
+// candidates and boxes that run all ten samples keep the warps equally full (the
+// one-pair-per-thread kernel above ran at 12.5 of 32 lanes).  mask /
+// near_mask are zeroed by the launcher; bits are set with atomicOr.
+template <int NDOF, bool MARGIN>
+__global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
+    swept_cc_steal_kernel(const __grid_constant__ RobotDev<double> rb, const SceneView<double> sc,
+                          const double* __restrict__ q0, const double* __restrict__ q1, int64_t n,
+                          int n_samples, bool vec, uint32_t* __restrict__ mask,
+                          uint32_t* __restrict__ near_mask, double margin,
+                          unsigned long long* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_scene = reinterpret_cast<double*>(smem_raw);
+  for (int k = threadIdx.x; k < sc.n * kSceneStride; k += blockDim.x) s_scene[k] = sc.boxes[k];
+  __syncthreads();
+  double* s_qa = s_scene + sc.n * kSceneStride;
+  double* s_qb = s_qa + NDOF * kTile;
+
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n_scene = sc.n;
+  int64_t idx = -1;  // -1: wants a pair, -2: the counter is exhausted
+  int slot = 0, b = 0, cur = 0, left = 0;  // slot in progress, next box, box being sampled, samples left
+  uint64_t cand = 0;
+  Tf<double> Wa;
+  double l[3] = {0.0, 0.0, 0.0}, angle = 0.0, ax[3] = {1.0, 0.0, 0.0};
+  Verdict<double, MARGIN> v;
+  Tf<double> Ta, Tb;
+  tf_load<double>(Ta, rb.base);
+  Tb = Ta;
+
+  while (true) {
+    const unsigned want = __ballot_sync(full, idx == -1);
+    if (want != 0) {
+      unsigned long long first = 0;
+      const int leader = __ffs((int)want) - 1;
+      if (lane == leader) first = atomicAdd(counter, (unsigned long long)__popc(want));
+      first = __shfl_sync(full, first, leader);
+      if (idx == -1) {
+        const int64_t mine = (int64_t)first + __popc(want & ((1u << lane) - 1u));
+        if (mine < n) {
+          idx = mine;
+          double qa[NDOF], qb[NDOF];
+          load_q_direct<double, NDOF>(qa, q0, idx, n, ACRO_Q_AOS, vec);
+          load_q_direct<double, NDOF>(qb, q1, idx, n, ACRO_Q_AOS, vec);
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i) {
+            s_qa[i * kTile + threadIdx.x] = qa[i];
+            s_qb[i * kTile + threadIdx.x] = qb[i];
+          }
+          v = Verdict<double, MARGIN>();
+          tf_load<double>(Ta, rb.base);
+          Tb = Ta;
+          base_slot_boxes<MARGIN>(rb, Ta, s_scene, n_scene, margin, v);  // robot.py:303-306
+          slot = 0;
+          b = rb.slot_begin[1];  // slot 0 is done: the first round opens slot 1
+          left = 0;
+        } else {
+          idx = -2;
+        }
+      }
+    }
+    if (__all_sync(full, idx == -2)) break;
+    if (idx >= 0) {
+      bool finished = false;
+      if (left == 0) {
+        // next box: close the slot when its boxes are used up (DH step of both chains), then
+        // set up one box; a box with candidates starts its n_samples sample rounds
+        if (b == rb.slot_begin[slot + 1]) {
+          ++slot;
+          if (slot > NDOF + 1 || n_scene == 0) {
+            finished = true;
+          } else {
+            if (slot <= NDOF) {
+              chain_step<double>(Ta, rb, slot - 1, s_qa[(slot - 1) * kTile + threadIdx.x]);
+              chain_step<double>(Tb, rb, slot - 1, s_qb[(slot - 1) * kTile + threadIdx.x]);
+            }
+            b = rb.slot_begin[slot];
+          }
+        }
+        if (!finished && b < rb.slot_begin[slot + 1]) {
+          cand = setup_moving_box(rb.boxes[b], Ta, Tb, s_scene, n_scene, MARGIN ? margin : 0.0, Wa,
+                                  l, angle, ax);
+          cur = b++;
+          if (cand != 0) left = n_samples;
+        }
+      } else {
+        sample_moving_box<MARGIN>(rb.boxes[cur], Wa, l, angle, ax, n_samples - left, n_samples,
+                                  cand, s_scene, margin, v);
+        --left;
+      }
+      if (v.done(margin) || finished) {
+        const uint32_t bit = 1u << (idx & 31);
+        if (v.hit) atomicOr(mask + (idx >> 5), bit);
+        if (MARGIN && v.gmin <= margin && v.gmin >= -margin) atomicOr(near_mask + (idx >> 5), bit);
+        idx = -1;
+      }
+    }
+  }
+}
+
+// counter: one zero-initialised 8-byte device word -> the persistent kernel; nullptr -> one
+// thread per pair
 cudaError_t launch_swept_cc(const RobotDev<double>& rb, SceneView<double> sc, const double* q0,
                             const double* q1, int64_t n, int n_samples, uint32_t* mask,
-                            uint32_t* near_mask, double margin, cudaStream_t st) {
+                            uint32_t* near_mask, double margin, unsigned long long* counter,
+                            cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffffLL || n_samples < 2) return cudaErrorInvalidValue;
+  if (counter) {
+    const size_t words = (size_t)((n + 31) / 32);
+    cudaError_t e = cudaMemsetAsync(mask, 0, sizeof(uint32_t) * words, st);
+    if (e == cudaSuccess && near_mask) e = cudaMemsetAsync(near_mask, 0, sizeof(uint32_t) * words, st);
+    if (e != cudaSuccess) return e;
+  }
   ACRO_DISPATCH_NDOF(rb.ndof, {
     const size_t smem = sizeof(double) * (sc.n * kSceneStride + 2 * NDOF * kTile);
     const bool vec = NDOF % 2 == 0 && aligned16(q0) && aligned16(q1);
-    if (near_mask)
+    if (counter) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int64_t resident = (int64_t)sms * ACRO_SWEPT_MIN_CTAS;
+      const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+      if (near_mask)
+        swept_cc_steal_kernel<NDOF, true><<<grid, kTile, smem, st>>>(
+            rb, sc, q0, q1, n, n_samples, vec, mask, near_mask, margin, counter);
+      else
+        swept_cc_steal_kernel<NDOF, false><<<grid, kTile, smem, st>>>(
+            rb, sc, q0, q1, n, n_samples, vec, mask, nullptr, 0.0, counter);
+    } else if (near_mask) {
       swept_cc_kernel<NDOF, true><<<(unsigned)tiles, kTile, smem, st>>>(
           rb, sc, q0, q1, n, n_samples, vec, mask, near_mask, margin);
-    else
+    } else {
       swept_cc_kernel<NDOF, false><<<(unsigned)tiles, kTile, smem, st>>>(
           rb, sc, q0, q1, n, n_samples, vec, mask, nullptr, 0.0);
+    }
   });
   count_launch();
   return cudaGetLastError();

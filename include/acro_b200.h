@@ -105,7 +105,10 @@ int acro_device_count(void);
  *                  without a near mask; all variants return identical verdicts;
  *   "k2_split"   = "auto" (default) | 0 | k: slot after which the filtered kernel regroups the
  *                  still undecided configurations into full warps (0 = single pass);
- *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 128).
+ *   "k2_grid"    = cells per axis of the candidate grid of the filtered kernel (default 128);
+ *   "swept_persistent" = "0" (default) | "1": acro_swept_cc_f64 runs one thread per pair, or
+ *                  (>= 4096 pairs) the persistent kernel whose lanes take pairs from a counter;
+ *                  identical verdicts, the persistent kernel measured slower.
  * The environment variables ACRO_K2_VARIANT / ACRO_K2_SPLIT / ACRO_K2_GRID set the initial values.    */
 int acro_set_option(const char* name, const char* value);
 

@@ -133,3 +133,32 @@ def test_edge_cases(gpu):
     gm = no.swept_margins(spec(arm), scene, q3, q4)
     ok = ~(near | (np.abs(gm) <= MARGIN))
     assert np.array_equal(hit[ok], ~(gm > 0)[ok])
+
+
+def test_persistent_and_per_thread_kernels_agree(gpu):
+    """The optional persistent kernel (lanes take pairs from a counter, one box set-up or one
+    sample per round, bits set with atomicOr) must give the same words as the default
+    one-thread-per-pair kernel."""
+    import torch
+
+    from acrobotics_b200 import _native
+
+    g = golden("ccd.npz")
+    scene = scene16()
+    for k, n in ((_kuka(g), 60_001), (ab.KukaOnRail(), 40_000), (ab.AnthropomorphicArm(), 5_000)):
+        qs = torch.as_tensor(random_configs(n, k.ndof, seed=41)).cuda()
+        qg = qs + (torch.rand_like(qs) * 2 - 1) * 1.5
+        want = k.is_path_in_collision_batch(qs, qg, scene, return_near=True, margin=MARGIN, packed=True)
+        want_plain = k.is_path_in_collision_batch(qs, qg, scene, packed=True)
+        _native.set_option("swept_persistent", "1")
+        try:
+            got = k.is_path_in_collision_batch(qs, qg, scene, return_near=True, margin=MARGIN, packed=True)
+            plain = k.is_path_in_collision_batch(qs, qg, scene, packed=True)
+            # an `out` buffer with stale bits: the words are rewritten, not ORed in
+            out = torch.full((n // 32 + 5,), -1, dtype=torch.int32, device="cuda")
+            k.is_path_in_collision_batch(qs, qg, scene, out=out)
+        finally:
+            _native.set_option("swept_persistent", "0")
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert torch.equal(plain, want_plain)
+        assert torch.equal(out[: (n + 31) // 32], plain) and bool((out[(n + 31) // 32:] == -1).all())
