@@ -94,6 +94,7 @@ SIGNATURES = {
     "acro_ik_anthropomorphic_f64": (C.c_int, [_D, _D, _P, _I64, _P, _P, _P]),
     "acro_ik_wrist_f64": (C.c_int, [_P, C.POINTER(_D), _I64, _P, _P]),
     "acro_path_cc_f64": (C.c_int, [_P, _P, _P, _P, _I64, _D, _P, _P]),
+    "acro_swept_boxes_f64": (C.c_int, [_P, _P, _P, _I64, C.c_int32, _P, _P]),
     "acro_swept_cc_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int32, _P, _P, _D, _P]),
     "acro_filter_tolerance": (C.c_int, [_P, _P, C.POINTER(_D)]),
     "acro_measure_filter_error": (C.c_int, [_P, _P, _P, _I64, _P, _P]),

@@ -75,6 +75,26 @@ def collide_box_pairs(boxes_a, boxes_b):
     return device.unpack_mask(words, n, host=True)
 
 
+def sweep_box_pairs(boxes_a_start, boxes_a_goal, boxes_b, n_samples=0):
+    """Row-wise swept test (``fcl.continuousCollide`` with CCDM_LINEAR, shapes.py:60-75): box a
+    moves from its start to its goal pose, box b is fixed; (n, 15) packed arrays -> bool (n,)."""
+    n = boxes_a_start.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=bool)
+    device.require_cuda()
+    lib = _native.load()
+    a0 = torch.from_numpy(np.ascontiguousarray(boxes_a_start)).cuda()
+    a1 = torch.from_numpy(np.ascontiguousarray(boxes_a_goal)).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(boxes_b)).cuda()
+    words = torch.empty(device.mask_words(n), dtype=torch.int32, device="cuda")
+    _native.check(
+        lib.acro_swept_boxes_f64(a0.data_ptr(), a1.data_ptr(), b.data_ptr(), n, int(n_samples),
+                                 words.data_ptr(), device.current_stream_ptr()),
+        "acro_swept_boxes_f64",
+    )
+    return device.unpack_mask(words, n, host=True)
+
+
 class Box:
     """Axis-aligned box in its own frame with side lengths ``dx, dy, dz``; it has
     no pose of its own (a transform is supplied with every query)."""
@@ -96,6 +116,13 @@ class Box:
         a = _pack_boxes([self], [tf])
         b = _pack_boxes([other], [tf_other])
         return int(collide_box_pairs(a, b)[0])
+
+    def is_path_in_collision(self, tf, tf_target, other, tf_other):
+        """``fcl.continuousCollide`` of this box moving from ``tf`` to ``tf_target`` against
+        the fixed ``other`` (shapes.py:60-75); stateless (the reference's result object
+        accumulates, see ``Robot.is_path_in_collision_batch``)."""
+        return bool(sweep_box_pairs(_pack_boxes([self], [tf]), _pack_boxes([self], [tf_target]),
+                                    _pack_boxes([other], [tf_other]))[0])
 
     # -- plain geometry (host side; plotting / optimisation helpers) ----------
     def get_vertices(self, tf):
@@ -154,6 +181,17 @@ class Scene:
             return False
         ia, ib = np.meshgrid(np.arange(len(a)), np.arange(len(b)), indexing="ij")
         return bool(collide_box_pairs(a[ia.ravel()], b[ib.ravel()]).any())
+
+    def is_path_in_collision(self, tf_self, tf_target, other, tf_other=None):
+        """Every shape of ``self`` as its own moving object between ``tf_self @ tf`` and
+        ``tf_target @ tf`` against every shape of ``other`` (geometry.py:68-81)."""
+        a0 = self.packed(tf_self)
+        a1 = self.packed(tf_target)
+        b = other.packed(tf_other)
+        if len(a0) == 0 or len(b) == 0:
+            return False
+        ia, ib = np.meshgrid(np.arange(len(a0)), np.arange(len(b)), indexing="ij")
+        return bool(sweep_box_pairs(a0[ia.ravel()], a1[ia.ravel()], b[ib.ravel()]).any())
 
     # -- device handle --------------------------------------------------------
     def native_handle(self):

@@ -1100,6 +1100,16 @@ int acro_ik_wrist_f64(const double* R, const double* R_base_host, int64_t n, dou
   return finish(launch_ik_wrist(R, R_base_host, n, q_out, as_stream(stream)), "acro_ik_wrist_f64");
 }
 
+int acro_swept_boxes_f64(const AcroBox* a_start, const AcroBox* a_goal, const AcroBox* b, int64_t n,
+                         int32_t n_samples, uint32_t* mask, void* stream) {
+  if (n < 0 || (n > 0 && (!a_start || !a_goal || !b || !mask)))
+    return fail(ACRO_E_INVALID, "bad arguments");
+  if (n_samples == 0) n_samples = 10;
+  if (n_samples < 2) return fail(ACRO_E_INVALID, "n_samples must be 0 (FCL's 10) or >= 2");
+  return finish(launch_swept_boxes(a_start, a_goal, b, n, n_samples, mask, as_stream(stream)),
+                "acro_swept_boxes_f64");
+}
+
 int acro_swept_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
                       const double* q_goal, int64_t n_pairs, int32_t n_samples, uint32_t* mask,
                       uint32_t* near_mask, double margin, void* stream) {

@@ -79,6 +79,9 @@ cudaError_t launch_swept_cc(const RobotDev<double>& rb, SceneView<double> sc, co
                             uint32_t* near_mask, double margin, unsigned long long* counter,
                             cudaStream_t st);
 
+cudaError_t launch_swept_boxes(const AcroBox* a0, const AcroBox* a1, const AcroBox* b, int64_t n,
+                               int n_samples, uint32_t* mask, cudaStream_t st);
+
 // filtered sweep (FP32 filter + exact FP64 pass over the ambiguous segments); `scratch` holds
 // 8 * ceil(ceil(n_seg / 32) / 2) + 8 bytes
 cudaError_t launch_path_cc_filter(const RobotDev<float>& rb32, const RobotDev<double>& rb64,

@@ -368,6 +368,58 @@ __global__ void __launch_bounds__(kTile, ACRO_SWEPT_MIN_CTAS)
   }
 }
 
+// n independent (moving box, fixed box) pairs: the fcl.continuousCollide seam itself
+// (shapes.py:60-75).  a0 / a1: the moving box at its start / target pose (same half extents).
+__global__ void __launch_bounds__(kTile)
+    swept_boxes_kernel(const AcroBox* __restrict__ a0, const AcroBox* __restrict__ a1,
+                       const AcroBox* __restrict__ b, int64_t n, int n_samples,
+                       uint32_t* __restrict__ mask) {
+  const int64_t idx = (int64_t)blockIdx.x * kTile + threadIdx.x;
+  bool hit = false;
+  if (idx < n) {
+    const AcroBox& A = a0[idx];
+    const AcroBox& A1 = a1[idx];
+    const AcroBox& B = b[idx];
+    double Ra[9], Rb[9], pa[3], l[3], ob[16];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Ra[3 * r + c] = A.tf[4 * r + c];
+        Rb[3 * r + c] = A1.tf[4 * r + c];
+        ob[kOB_R + 3 * r + c] = B.tf[4 * r + c];
+      }
+      pa[r] = A.tf[4 * r + 3];
+      l[r] = A1.tf[4 * r + 3] - pa[r];
+      ob[kOB_T + r] = B.tf[4 * r + 3];
+      ob[kOB_H + r] = B.half[r];
+    }
+    double angle, ax[3];
+    relative_angle_axis(Ra, Rb, angle, ax);
+    for (int s = 0; s < n_samples && !hit; ++s) {
+      const double t = (double)s / (double)(n_samples - 1);
+      double R[9], c[3], g;
+      rotate_about(ax, t * angle, Ra, R);
+      c[0] = fma(t, l[0], pa[0]);
+      c[1] = fma(t, l[1], pa[1]);
+      c[2] = fma(t, l[2], pa[2]);
+      hit = !sat_separated<double>(A.half[0], A.half[1], A.half[2], R, c, ob, 0.0, g);
+    }
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && idx < n) mask[idx >> 5] = word;
+}
+
+cudaError_t launch_swept_boxes(const AcroBox* a0, const AcroBox* a1, const AcroBox* b, int64_t n,
+                               int n_samples, uint32_t* mask, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffLL || n_samples < 2) return cudaErrorInvalidValue;
+  swept_boxes_kernel<<<(unsigned)tiles, kTile, 0, st>>>(a0, a1, b, n, n_samples, mask);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // counter: one zero-initialised 8-byte device word -> the persistent kernel; nullptr -> one
 // thread per pair
 cudaError_t launch_swept_cc(const RobotDev<double>& rb, SceneView<double> sc, const double* q0,

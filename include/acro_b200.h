@@ -264,6 +264,12 @@ int acro_path_cc_f64(const AcroRobot* robot, const AcroScene* scene, const doubl
  * no self collision.  mask bit e = the pair collides.  near_mask (or NULL) / margin as in
  * acro_fk_cc_f64.  Stateless: the reference's python-fcl result object is sticky per
  * Shape.                                                          */
+/* The fcl.continuousCollide seam itself: Shape.is_path_in_collision (shapes.py:60-75) for n
+ * independent pairs - box a moves from a_start[i] to a_goal[i] (same half extents; FCL's
+ * InterpMotion, n_samples samples, 0 = 10), box b[i] is fixed.  mask bit i = they collide at
+ * some sample.                                                                            */
+int acro_swept_boxes_f64(const AcroBox* a_start, const AcroBox* a_goal, const AcroBox* b, int64_t n,
+                         int32_t n_samples, uint32_t* mask, void* stream);
 int acro_swept_cc_f64(const AcroRobot* robot, const AcroScene* scene, const double* q_start,
                       const double* q_goal, int64_t n_pairs, int32_t n_samples, uint32_t* mask,
                       uint32_t* near_mask, double margin, void* stream);

@@ -162,3 +162,40 @@ def test_persistent_and_per_thread_kernels_agree(gpu):
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
         assert torch.equal(plain, want_plain)
         assert torch.equal(out[: (n + 31) // 32], plain) and bool((out[(n + 31) // 32:] == -1).all())
+
+
+def test_shape_level_seam(gpu):
+    """``Shape.is_path_in_collision`` / ``ShapeSoup.is_path_in_collision`` (shapes.py:60-75,
+    geometry.py:68-81): the box-level entry point against the scalar FCL restatement, and the
+    robot-level verdict recomposed from it the way robot.py:285-317 does."""
+    from oracle import fcl_ccd
+
+    rng = np.random.default_rng(8)
+
+    def rand_tf(scale):
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        R *= np.sign(np.linalg.det(R))
+        tf = np.eye(4)
+        tf[:3, :3], tf[:3, 3] = R, rng.uniform(-scale, scale, 3)
+        return tf
+
+    n_hit = 0
+    for _ in range(60):
+        a, b = ab.Box(*rng.uniform(0.1, 0.6, 3)), ab.Box(*rng.uniform(0.1, 0.6, 3))
+        t0, t1, tb = rand_tf(0.6), rand_tf(0.6), rand_tf(0.3)
+        want, _, g = fcl_ccd.continuous_collide_boxes(
+            [a.dx, a.dy, a.dz], t0[:3, :3], t0[:3, 3], t1[:3, :3], t1[:3, 3],
+            [b.dx, b.dy, b.dz], tb[:3, :3], tb[:3, 3])
+        if abs(g) > 1e-6:
+            assert a.is_path_in_collision(t0, t1, b, tb) == want
+            n_hit += want
+    assert 5 < n_hit < 55
+    # the robot-level query recomposed from the soup-level one (links only: a bare Kuka)
+    k = ab.Kuka()
+    g = golden("ccd.npz")
+    scene = product_scene(g["s3_sides"], g["s3_tfs"])
+    for i in range(12):
+        qs, qg = g["s3_q_start"][i], g["s3_q_goal"][i]
+        fa, fb = k.fk_all_links(qs), k.fk_all_links(qg)
+        want = any(l.geometry.is_path_in_collision(fa[j], fb[j], scene) for j, l in enumerate(k.links))
+        assert k.is_path_in_collision(qs, qg, scene) == want
