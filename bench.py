@@ -445,6 +445,23 @@ def run_ours(args):
                  "n_gpus": world, "partition": "contiguous word-aligned pair blocks per rank",
                  "collective": "in-place all-gather of the verdict words",
                  "path": "sharding.is_path_in_collision_sharded -> acro_swept_cc_f64 (FP64)"}
+        if rank == 0 and not args.no_parity:
+            # the timed verdicts of the first pairs against the oracle's restatement of
+            # fcl.continuousCollide (numpy, host), with the near-contact bucket of the margin mode
+            import numpy as _np
+
+            from oracle import np_oracle as _no
+
+            m = min(E, args.swept_parity_pairs)
+            a_h, b_h = qs_sw[:m].cpu().numpy(), qg_sw[:m].cpu().numpy()
+            _, near = robot.is_path_in_collision_batch(a_h, b_h, scene, return_near=True, margin=1e-6)
+            timed = _np.unpackbits(res["w"][: (m + 31) // 32].cpu().numpy().view(_np.uint8),
+                                   bitorder="little")[:m].astype(bool)
+            gsw = _no.swept_margins(_no.spec_from_robot(robot), scene, a_h, b_h)
+            bucket = near | (_np.abs(gsw) <= 1e-6)
+            swept["parity"] = {"pairs_checked": m, "oracle": "oracle/np_oracle.swept_margins (numpy)",
+                               "mismatches_outside_margin": int(((timed != ~(gsw > 0)) & ~bucket).sum()),
+                               "margin_bucket": int(bucket.sum()), "margin_m": 1e-6}
         del qs_sw, qg_sw, res
 
     # ---- C2 / C4 (single-GPU configs; reported at N = 1)
@@ -646,6 +663,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-swept", action="store_true")
     ap.add_argument("--swept-pairs", type=int, default=2_000_000)
+    ap.add_argument("--swept-parity-pairs", type=int, default=3000)
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-c24", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
