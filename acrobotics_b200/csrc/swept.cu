@@ -199,8 +199,11 @@ __device__ __forceinline__ void base_slot_boxes(const RobotDev<double>& rb, cons
   }
 }
 
+// 4 CTAs of 128 threads per SM (128 registers, some spills to the stack): measured best on the
+// rolled kernel - 2 / 3 / 4 / 5 / 6 / 8 CTAs: 7.03 / 6.13 / 5.69 / 5.67 / 5.94 / 7.36 ms per 4 M pairs
+// (profiles/r2_swept_ab.jsonl); the FP64 chains need the extra warps to hide their latency
 #ifndef ACRO_SWEPT_MIN_CTAS
-#define ACRO_SWEPT_MIN_CTAS 2
+#define ACRO_SWEPT_MIN_CTAS 4
 #endif
 
 template <int NDOF, bool MARGIN>
