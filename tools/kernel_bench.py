@@ -228,6 +228,11 @@ def main():
         b, a = timed(f, args.reps)
         steps = torch.ceil(torch.linalg.norm(qg - qs, dim=1) / 0.1).sum().item()
         emit("path_cc_f64[scene16]", b, a, e, None, {"interpolants_upper_bound_per_s": steps / (b * 1e-3)})
+        # K7: swept collision of the same segments (ten FCL motion samples per box, all FP64)
+        f = lambda: _native.check(lib.acro_swept_cc_f64(hfull, hs, qs.data_ptr(), qg.data_ptr(), e, 0,  # noqa: E731
+                                                        mask.data_ptr(), None, 0.0, stream))
+        b, a = timed(f, args.reps)
+        emit("swept_cc_f64[scene16]", b, a, e, None, {"pose_checks_per_s": 10 * e / (b * 1e-3)})
 
 
 if __name__ == "__main__":
